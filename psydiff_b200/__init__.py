@@ -1,0 +1,10 @@
+"""psydiff_b200 — B200-native SR-UKF likelihood / finite-difference gradient path of jhorzek/psydiff.
+
+Host-side mirror of the reference's R API (same names) over the C ABI of ``libpsydiff_b200.so``.
+"""
+from ._lib import PsydiffError  # noqa: F401
+from .model import (  # noqa: F401
+    newPsydiff, compileModel, compileModelSource, fitModel, getGradients, getGradient, getGradientsParallel,
+    compileParallelGradients, stopParallelGradients, getParameterValues, setParameterValues, clonePsydiffModel,
+    sdeModelMatrix, sepNameFromValue, chol2LogChol, extractParameters, makeGroups, checkEquation,
+)

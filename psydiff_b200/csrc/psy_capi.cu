@@ -1,0 +1,733 @@
+// psy_capi.cu — libpsydiff_b200.so: the C ABI declared in include/psydiff_b200.h.
+//
+// Host orchestration around the generated filter kernel (psy_filter.cuh): model compile/load, dataset residency
+// in HBM, the integer slot map that replaces psydiff's string-keyed parameterTable (inst/include/psydiffBasic.h),
+// the (person x perturbation) instance list that folds getGradients' 2P+1 fitModel sweeps
+// (R/modelTemplate.R:852-930) into one launch, and K3 — the deterministic per-parameter reduction.
+// There is NO CPU fallback in this file: without a device every compute entry point returns PSY_ERR_CUDA.
+#include "../../include/psydiff_b200.h"
+#include "psy_launch.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace {
+
+thread_local std::string g_err;
+long long g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[4096];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess) return fail(PSY_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+// ---- driver entry points, resolved through the runtime so the library carries no link-time libcuda dependency
+struct Drv {
+  CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+  CUresult (*ModuleUnload)(CUmodule) = nullptr;
+  CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+  CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+  CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  bool ok = false;
+};
+Drv g_drv;
+
+int load_driver() {
+  if (g_drv.ok) return PSY_OK;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(PSY_ERR_CUDA, "no CUDA device available (%s); libpsydiff_b200 has no CPU fallback", cudaGetErrorString(e));
+  CU_TRY(cudaFree(0));
+  struct { const char* name; void** slot; } tab[] = {
+      {"cuModuleLoadData", (void**)&g_drv.ModuleLoadData}, {"cuModuleUnload", (void**)&g_drv.ModuleUnload},
+      {"cuModuleGetFunction", (void**)&g_drv.ModuleGetFunction}, {"cuLaunchKernel", (void**)&g_drv.LaunchKernel},
+      {"cuFuncGetAttribute", (void**)&g_drv.FuncGetAttribute}, {"cuGetErrorString", (void**)&g_drv.GetErrorString}};
+  for (auto& t : tab) {
+    cudaDriverEntryPointQueryResult qr;
+    cudaError_t ee = cudaGetDriverEntryPoint(t.name, t.slot, cudaEnableDefault, &qr);
+    if (ee != cudaSuccess || qr != cudaDriverEntryPointSuccess || !*t.slot)
+      return fail(PSY_ERR_CUDA, "cannot resolve driver entry point %s", t.name);
+  }
+  g_drv.ok = true;
+  return PSY_OK;
+}
+
+const char* cu_str(CUresult r) {
+  const char* s = nullptr;
+  if (g_drv.GetErrorString) g_drv.GetErrorString(r, &s);
+  return s ? s : "unknown driver error";
+}
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    if (count <= n && p) return PSY_OK;
+    release();
+    if (count == 0) count = 1;
+    CU_TRY(cudaMalloc((void**)&p, count * sizeof(T)));
+    n = count;
+    return PSY_OK;
+  }
+  int upload(const T* h, size_t count) {
+    int rc = alloc(count);
+    if (rc) return rc;
+    if (count) CU_TRY(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice));
+    return PSY_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+struct Chunk { int theta; int start; int len; int pad; };
+
+}  // namespace
+
+struct psy_model {
+  int n = 0, m = 0, F = 0, P = 0, N = 0;
+  int64_t rows = 0;
+  // settings
+  double alpha = .2, beta = 2.0, kappa = 0.0;
+  int stepper = PSY_STEPPER_RK4, sr = 1;
+  std::vector<double> time_step;
+  // module
+  CUmodule mod = nullptr;
+  CUfunction fn = nullptr;
+  // host copies
+  std::vector<double> h_dt;
+  std::vector<int64_t> h_row_off;
+  std::vector<int> h_tidx;           // N x F
+  std::vector<int64_t> h_inst_off;   // N+1
+  std::vector<int> h_dl;             // distinct theta lists, flattened at (inst_off[p]-p... ) see set_slots
+  std::vector<int64_t> h_dl_off;     // N+1
+  std::vector<int64_t> h_seg_off;    // P+1 (pairs per theta)
+  std::vector<int> h_pair_minus;     // instance index of the (p, theta, -) instance, sorted by theta then person
+  double ksteps_h = -1.0;
+  // device
+  DevBuf<double> d_obs, d_dt, d_theta, d_f, d_latent, d_pred, d_chunk_part, d_partial;
+  DevBuf<int> d_ksteps, d_pid, d_tidx, d_pair_minus, d_pair_base, d_out_idx, d_theta_chunk_off;
+  DevBuf<long long> d_row_off;
+  DevBuf<PsyInst> d_inst, d_inst_sub, d_inst_base;
+  DevBuf<Chunk> d_chunks;
+  int64_t n_inst = 0, n_chunks = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double last_ms = 0.0;
+  int64_t last_instances = 0;
+  // gradient sweep state (psy_grad_resolve)
+  double base_total = 0.0, base_nonfinite = 0.0;
+  std::vector<double> Dval;      // [P*2]
+  std::vector<double> eps_used;  // [P]
+  std::vector<unsigned char> resolved;  // [P*2]
+  std::vector<unsigned char> wanted;    // [P*2] sides the current sweep asks for
+};
+
+// =================================================================================================================
+// K3: deterministic reduction of instance results into per-parameter sums
+// =================================================================================================================
+namespace {
+
+__device__ __forceinline__ bool finite_d(double x) { return isfinite(x); }
+
+// one block per chunk (theta, start, len): fixed thread->entry assignment and a fixed shared-memory tree, so the
+// result is bit-reproducible run to run.  theta == P is the pseudo-segment of base instances (Σ f0).
+__global__ void __launch_bounds__(256) psy_reduce_chunks(const Chunk* __restrict__ chunks, const int* __restrict__ pair_minus,
+                                                         const int* __restrict__ pair_base, const double* __restrict__ f,
+                                                         int P, double* __restrict__ chunk_part) {
+  __shared__ double sh[5][256];
+  const Chunk c = chunks[blockIdx.x];
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+  for (int e = threadIdx.x; e < c.len; e += 256) {
+    const int idx = c.start + e;
+    const int ib = pair_base[idx];
+    const double f0 = f[ib];
+    if (c.theta == P) {
+      a0 += f0;
+      a1 += finite_d(f0) ? 0.0 : 1.0;
+    } else {
+      const int im = pair_minus[idx];
+      const double fm = f[im], fp = f[im + 1];
+      const double f0s = finite_d(f0) ? f0 : 0.0;
+      a0 += fp - f0s;                      // D+
+      a1 += fm - f0s;                      // D-
+      a2 += finite_d(fp) ? 0.0 : 1.0;      // nf+
+      a3 += finite_d(fm) ? 0.0 : 1.0;      // nf-
+      a4 += finite_d(f0) ? 0.0 : 1.0;      // nbt
+    }
+  }
+  sh[0][threadIdx.x] = a0; sh[1][threadIdx.x] = a1; sh[2][threadIdx.x] = a2; sh[3][threadIdx.x] = a3; sh[4][threadIdx.x] = a4;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+#pragma unroll
+      for (int q = 0; q < 5; q++) sh[q][threadIdx.x] += sh[q][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 5) chunk_part[(size_t)blockIdx.x * 5 + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+// one thread per theta (and one for the base pseudo-segment): sequential sum of its chunks' partials
+__global__ void psy_reduce_final(const int* __restrict__ theta_chunk_off, const double* __restrict__ chunk_part, int P,
+                                 double* __restrict__ partial) {
+  const int th = blockIdx.x * blockDim.x + threadIdx.x;
+  if (th > P) return;
+  double a[5] = {0, 0, 0, 0, 0};
+  for (int c = theta_chunk_off[th]; c < theta_chunk_off[th + 1]; c++)
+    for (int q = 0; q < 5; q++) a[q] += chunk_part[(size_t)c * 5 + q];
+  if (th == P) {
+    partial[0] = a[0];
+    partial[1] = a[1];
+  } else {
+    partial[2 + th] = a[0];
+    partial[2 + (size_t)P + th] = a[1];
+    partial[2 + 2 * (size_t)P + th] = a[2];
+    partial[2 + 3 * (size_t)P + th] = a[3];
+    partial[2 + 4 * (size_t)P + th] = a[4];
+  }
+}
+
+// row-major [rows][k] -> column-major rows x k (R matrix layout) on the device, coalesced on the write side
+__global__ void psy_to_colmajor(const double* __restrict__ src, double* __restrict__ dst, long long rows, int k) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * k) return;
+  const long long r = i % rows;
+  const int c = (int)(i / rows);
+  dst[i] = src[r * k + c];
+}
+
+// dependent-free DFMA stream: 8 independent accumulators per thread, the FP64 roofline denominator
+__global__ void __launch_bounds__(256) psy_dfma_peak(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+uint64_t fnv1a(const std::string& s, uint64_t h = 1469598103934665603ULL) {
+  for (unsigned char c : s) { h ^= c; h *= 1099511628211ULL; }
+  return h;
+}
+
+std::string slurp(const std::string& path) {
+  std::ifstream f(path, std::ios::binary);
+  std::stringstream ss;
+  ss << f.rdbuf();
+  return ss.str();
+}
+
+bool file_exists(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 && st.st_size > 0; }
+
+// odeint integrate_const step count, rule T1: exact IEEE, evaluated on the host once per distinct dt
+int rk4_step_count(double t1, double h) {
+  if (!(h > 0) || !(t1 == t1)) return 0;
+  int step = 0;
+  double time = 0.0;
+  while ((time + h) - t1 <= DBL_EPSILON) {
+    ++step;
+    time = 0.0 + (double)step * h;
+    if (step > 50000000) break;
+  }
+  return step;
+}
+
+int ensure_ksteps(psy_model* M) {
+  const double h = M->time_step.empty() ? 0.0 : M->time_step[0];
+  if (M->ksteps_h == h && M->d_ksteps.p) return PSY_OK;
+  std::vector<int> ks(M->rows);
+  std::unordered_map<double, int> cache;
+  for (int64_t r = 0; r < M->rows; r++) {
+    const double d = M->h_dt[r];
+    auto it = cache.find(d);
+    if (it == cache.end()) it = cache.emplace(d, rk4_step_count(d, h)).first;
+    ks[r] = it->second;
+  }
+  int rc = M->d_ksteps.upload(ks.data(), ks.size());
+  if (rc) return rc;
+  M->ksteps_h = h;
+  return PSY_OK;
+}
+
+int launch_filter(psy_model* M, const PsyInst* d_list, const int* d_out_idx, int64_t count, double eps, int skip_update,
+                  double* d_latent, double* d_pred) {
+  if (!M->fn) return fail(PSY_ERR_STATE, "model module not loaded");
+  if (!M->d_obs.p) return fail(PSY_ERR_STATE, "psy_upload has not been called");
+  if (!M->d_tidx.p) return fail(PSY_ERR_STATE, "psy_set_slots has not been called");
+  if (M->time_step.empty()) return fail(PSY_ERR_STATE, "psy_model_settings has not been called");
+  if (count <= 0) return PSY_OK;
+  if (count > 2147483000LL) return fail(PSY_ERR_ARG, "too many instances for one launch (%lld)", (long long)count);
+  int rc = ensure_ksteps(M);
+  if (rc) return rc;
+  double kappa = M->kappa;
+  if (M->n + kappa == 0) kappa -= 1;  // R/modelTemplate.R:192-196
+  const double lambda = M->alpha * M->alpha * (M->n + kappa) - M->n;
+  PsyLaunch L;
+  memset(&L, 0, sizeof L);
+  L.obs = M->d_obs.p; L.dt = M->d_dt.p; L.ksteps = M->d_ksteps.p; L.row_off = M->d_row_off.p;
+  L.person_id = M->d_pid.p; L.theta_index = M->d_tidx.p; L.theta = M->d_theta.p; L.inst = d_list;
+  L.f_out = M->d_f.p; L.out_idx = d_out_idx; L.latent = d_latent; L.pred = d_pred;
+  L.eps = eps; L.h = M->time_step[0];
+  L.c = M->alpha * M->alpha * (M->n + kappa);
+  L.sqrtc = sqrt(L.c);
+  L.wm0 = lambda / (M->n + lambda);
+  L.wm1 = 1 / (2 * (M->n + lambda));
+  L.wc0 = lambda / (M->n + lambda) + (1 - M->alpha * M->alpha + M->beta);
+  L.wc1 = L.wm1;
+  L.n_inst = (int)count;
+  L.skip_update = skip_update;
+  const unsigned block = 128;
+  const unsigned grid = (unsigned)((count + block - 1) / block);
+  void* args[] = {&L};
+  CU_TRY(cudaEventRecord(M->ev0, 0));
+  CUresult r = g_drv.LaunchKernel(M->fn, grid, 1, 1, block, 1, 1, 0, (CUstream)0, args, nullptr);
+  if (r != CUDA_SUCCESS) return fail(PSY_ERR_CUDA, "cuLaunchKernel(psy_filter_kernel): %s", cu_str(r));
+  CU_TRY(cudaEventRecord(M->ev1, 0));
+  g_launches++;
+  CU_TRY(cudaEventSynchronize(M->ev1));
+  float ms = 0;
+  CU_TRY(cudaEventElapsedTime(&ms, M->ev0, M->ev1));
+  M->last_ms = ms;
+  M->last_instances = count;
+  CU_TRY(cudaGetLastError());
+  return PSY_OK;
+}
+
+int run_reduction(psy_model* M) {
+  if (M->n_chunks > 0) {
+    psy_reduce_chunks<<<(unsigned)M->n_chunks, 256>>>(M->d_chunks.p, M->d_pair_minus.p, M->d_pair_base.p, M->d_f.p, M->P,
+                                                      M->d_chunk_part.p);
+    g_launches++;
+  }
+  psy_reduce_final<<<(M->P + 1 + 127) / 128, 128>>>(M->d_theta_chunk_off.p, M->d_chunk_part.p, M->P, M->d_partial.p);
+  g_launches++;
+  CU_TRY(cudaGetLastError());
+  return PSY_OK;
+}
+
+}  // namespace
+
+// =================================================================================================================
+extern "C" {
+
+const char* psy_last_error(void) { return g_err.c_str(); }
+int psy_version(void) { return 100; }
+
+int psy_model_compile(const char* cuda_source, const char* include_dir, const char* cache_dir, const char* extra_flags,
+                      char* cubin_path, size_t cap) {
+  if (!cuda_source || !include_dir || !cache_dir || !cubin_path) return fail(PSY_ERR_ARG, "psy_model_compile: null argument");
+  const std::string inc(include_dir), cache(cache_dir), flags(extra_flags ? extra_flags : "");
+  uint64_t h = fnv1a(cuda_source);
+  for (const char* hdr : {"/psy_filter.cuh", "/psy_lang.cuh", "/psy_launch.h"}) {
+    std::string body = slurp(inc + hdr);
+    if (body.empty()) return fail(PSY_ERR_COMPILE, "kernel header %s%s not found", include_dir, hdr);
+    h = fnv1a(body, h);
+  }
+  h = fnv1a(flags, h);
+  char name[64];
+  snprintf(name, sizeof name, "psy_%016llx", (unsigned long long)h);
+  mkdir(cache.c_str(), 0755);
+  const std::string cu = cache + "/" + name + ".cu", cubin = cache + "/" + name + ".cubin", log = cache + "/" + name + ".log";
+  if (cubin.size() + 1 > cap) return fail(PSY_ERR_ARG, "cubin_path buffer too small");
+  if (!file_exists(cubin)) {
+    {
+      std::ofstream f(cu);
+      f << cuda_source;
+      if (!f) return fail(PSY_ERR_COMPILE, "cannot write %s", cu.c_str());
+    }
+    const char* nvcc_env = getenv("PSY_NVCC");
+    std::string nvcc = nvcc_env ? nvcc_env : (file_exists("/usr/local/cuda/bin/nvcc") ? "/usr/local/cuda/bin/nvcc" : "nvcc");
+    const std::string tmp = cubin + ".tmp" + std::to_string((long long)getpid());
+    std::string cmd = nvcc + " -cubin -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xptxas -v -I" + inc + " " +
+                      flags + " -o " + tmp + " " + cu + " > " + log + " 2>&1";
+    int rc = system(cmd.c_str());
+    if (rc != 0 || !file_exists(tmp)) {
+      std::string msg = slurp(log);
+      if (msg.size() > 3000) msg = msg.substr(0, 3000) + "\n...";
+      remove(tmp.c_str());
+      return fail(PSY_ERR_COMPILE,
+                  "model does not compile for the device (statements outside the supported equation subset are "
+                  "unsupported on device):\n%s", msg.c_str());
+    }
+    if (rename(tmp.c_str(), cubin.c_str()) != 0) return fail(PSY_ERR_COMPILE, "cannot move %s into the cache", tmp.c_str());
+  }
+  strcpy(cubin_path, cubin.c_str());
+  return PSY_OK;
+}
+
+psy_model* psy_model_create(int n, int m, int nfree, const char* cubin_path) {
+  if (n < 1 || m < 1 || nfree < 0 || !cubin_path) { fail(PSY_ERR_ARG, "psy_model_create: bad arguments"); return nullptr; }
+  if (load_driver()) return nullptr;
+  std::string image = slurp(cubin_path);
+  if (image.empty()) { fail(PSY_ERR_ARG, "cannot read compiled module %s", cubin_path); return nullptr; }
+  psy_model* M = new psy_model;
+  M->n = n; M->m = m; M->F = nfree;
+  CUresult r = g_drv.ModuleLoadData(&M->mod, image.data());
+  if (r != CUDA_SUCCESS) { fail(PSY_ERR_CUDA, "cuModuleLoadData(%s): %s", cubin_path, cu_str(r)); delete M; return nullptr; }
+  r = g_drv.ModuleGetFunction(&M->fn, M->mod, "psy_filter_kernel");
+  if (r != CUDA_SUCCESS) { fail(PSY_ERR_CUDA, "psy_filter_kernel not found in %s: %s", cubin_path, cu_str(r)); g_drv.ModuleUnload(M->mod); delete M; return nullptr; }
+  cudaEventCreate(&M->ev0);
+  cudaEventCreate(&M->ev1);
+  return M;
+}
+
+void psy_model_destroy(psy_model* M) {
+  if (!M) return;
+  M->d_obs.release(); M->d_dt.release(); M->d_theta.release(); M->d_f.release(); M->d_latent.release(); M->d_pred.release();
+  M->d_chunk_part.release(); M->d_partial.release(); M->d_ksteps.release(); M->d_pid.release(); M->d_tidx.release();
+  M->d_pair_minus.release(); M->d_pair_base.release(); M->d_out_idx.release(); M->d_theta_chunk_off.release();
+  M->d_row_off.release(); M->d_inst.release(); M->d_inst_sub.release(); M->d_inst_base.release(); M->d_chunks.release();
+  if (M->ev0) cudaEventDestroy(M->ev0);
+  if (M->ev1) cudaEventDestroy(M->ev1);
+  if (M->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(M->mod);
+  delete M;
+}
+
+int psy_model_settings(psy_model* M, double alpha, double beta, double kappa, int stepper, const double* ts, int n_ts, int sr) {
+  if (!M || !ts || n_ts < 1) return fail(PSY_ERR_ARG, "psy_model_settings: bad arguments");
+  if (stepper < 0 || stepper > 2) return fail(PSY_ERR_ARG, "unknown integrateFunction code %d", stepper);
+  M->alpha = alpha; M->beta = beta; M->kappa = kappa; M->stepper = stepper; M->sr = sr;
+  M->time_step.assign(ts, ts + n_ts);
+  return PSY_OK;
+}
+
+int psy_upload(psy_model* M, int64_t rows, int N, const double* obs_cm, const double* dt, const int64_t* person_off, const int* person_id) {
+  if (!M || rows < 1 || N < 1 || !obs_cm || !dt || !person_off || !person_id) return fail(PSY_ERR_ARG, "psy_upload: bad arguments");
+  if (person_off[0] != 0 || person_off[N] != rows) return fail(PSY_ERR_ARG, "psy_upload: person_off must run from 0 to rows");
+  for (int p = 0; p < N; p++)
+    if (person_off[p + 1] <= person_off[p]) return fail(PSY_ERR_ARG, "psy_upload: person %d has no rows", p);
+  const int m = M->m;
+  // R's column-major rows x m  ->  row-major [rows][m], so one time point is m contiguous doubles in HBM
+  std::vector<double> rm((size_t)rows * m);
+  for (int j = 0; j < m; j++)
+    for (int64_t r = 0; r < rows; r++) rm[(size_t)r * m + j] = obs_cm[(size_t)j * rows + r];
+  int rc;
+  if ((rc = M->d_obs.upload(rm.data(), rm.size()))) return rc;
+  if ((rc = M->d_dt.upload(dt, rows))) return rc;
+  std::vector<long long> ro(person_off, person_off + N + 1);
+  if ((rc = M->d_row_off.upload(ro.data(), ro.size()))) return rc;
+  if ((rc = M->d_pid.upload(person_id, N))) return rc;
+  M->h_dt.assign(dt, dt + rows);
+  M->h_row_off.assign(person_off, person_off + N + 1);
+  M->rows = rows; M->N = N; M->ksteps_h = -1.0;
+  M->d_tidx.release();  // a new dataset invalidates the slot map
+  M->n_inst = 0;
+  return PSY_OK;
+}
+
+int psy_set_slots(psy_model* M, int P, const int* tidx) {
+  if (!M || P < 0 || (M->F > 0 && !tidx)) return fail(PSY_ERR_ARG, "psy_set_slots: bad arguments");
+  if (M->N < 1) return fail(PSY_ERR_STATE, "psy_set_slots: call psy_upload first");
+  const int N = M->N, F = M->F;
+  for (size_t i = 0; i < (size_t)N * F; i++)
+    if (tidx[i] < 0 || tidx[i] >= P) return fail(PSY_ERR_ARG, "psy_set_slots: theta_index[%zu] = %d out of range [0,%d)", i, tidx[i], P);
+  M->P = P;
+  M->h_tidx.assign(tidx, tidx + (size_t)N * F);
+  // distinct theta per person, in slot order
+  M->h_dl.clear(); M->h_dl_off.assign(N + 1, 0); M->h_inst_off.assign(N + 1, 0);
+  std::vector<int64_t> cnt(P + 1, 0);
+  for (int p = 0; p < N; p++) {
+    const int* row = tidx + (size_t)p * F;
+    size_t b = M->h_dl.size();
+    for (int k = 0; k < F; k++) {
+      bool seen = false;
+      for (size_t q = b; q < M->h_dl.size(); q++) if (M->h_dl[q] == row[k]) { seen = true; break; }
+      if (!seen) { M->h_dl.push_back(row[k]); cnt[row[k]]++; }
+    }
+    M->h_dl_off[p + 1] = (int64_t)M->h_dl.size();
+    M->h_inst_off[p + 1] = M->h_inst_off[p] + 1 + 2 * (int64_t)(M->h_dl.size() - b);
+  }
+  M->n_inst = M->h_inst_off[N];
+  if (M->n_inst > 2147483000LL) return fail(PSY_ERR_ARG, "instance count %lld exceeds the per-rank limit; shard persons over more ranks", (long long)M->n_inst);
+  std::vector<PsyInst> inst((size_t)M->n_inst), base((size_t)N);
+  M->h_seg_off.assign(P + 1, 0);
+  for (int t = 0; t < P; t++) M->h_seg_off[t + 1] = M->h_seg_off[t] + cnt[t];
+  const int64_t n_pairs = M->h_seg_off[P];
+  std::vector<int> pair_minus((size_t)n_pairs + N), pair_base((size_t)n_pairs + N);
+  std::vector<int64_t> fill(M->h_seg_off.begin(), M->h_seg_off.end() - 1);
+  for (int p = 0; p < N; p++) {
+    int64_t o = M->h_inst_off[p];
+    inst[o] = PsyInst{p, -1};
+    base[p] = PsyInst{p, -1};
+    int64_t j = 0;
+    for (int64_t q = M->h_dl_off[p]; q < M->h_dl_off[p + 1]; q++, j++) {
+      const int t = M->h_dl[q];
+      inst[o + 1 + 2 * j] = PsyInst{p, (t << 1) | 0};
+      inst[o + 2 + 2 * j] = PsyInst{p, (t << 1) | 1};
+      pair_minus[fill[t]] = (int)(o + 1 + 2 * j);
+      pair_base[fill[t]] = (int)o;
+      fill[t]++;
+    }
+    pair_minus[n_pairs + p] = (int)o;  // base pseudo-segment (theta == P)
+    pair_base[n_pairs + p] = (int)o;
+  }
+  M->h_pair_minus.assign(pair_minus.begin(), pair_minus.begin() + n_pairs);
+  // chunk list
+  const int CH = 4096;
+  std::vector<Chunk> chunks;
+  std::vector<int> tco(P + 2, 0);
+  for (int t = 0; t <= P; t++) {
+    const int64_t s0 = (t < P) ? M->h_seg_off[t] : n_pairs, s1 = (t < P) ? M->h_seg_off[t + 1] : n_pairs + N;
+    tco[t] = (int)chunks.size();
+    for (int64_t s = s0; s < s1; s += CH) chunks.push_back(Chunk{t, (int)s, (int)std::min<int64_t>(CH, s1 - s), 0});
+  }
+  tco[P + 1] = (int)chunks.size();
+  M->n_chunks = (int64_t)chunks.size();
+  int rc;
+  if ((rc = M->d_tidx.upload(M->h_tidx.data(), M->h_tidx.size()))) return rc;
+  if ((rc = M->d_inst.upload(inst.data(), inst.size()))) return rc;
+  if ((rc = M->d_inst_base.upload(base.data(), base.size()))) return rc;
+  if ((rc = M->d_pair_minus.upload(pair_minus.data(), pair_minus.size()))) return rc;
+  if ((rc = M->d_pair_base.upload(pair_base.data(), pair_base.size()))) return rc;
+  if ((rc = M->d_chunks.upload(chunks.data(), chunks.size()))) return rc;
+  if ((rc = M->d_theta_chunk_off.upload(tco.data(), tco.size()))) return rc;
+  if ((rc = M->d_chunk_part.alloc(chunks.size() * 5))) return rc;
+  if ((rc = M->d_partial.alloc(5 * (size_t)P + 2))) return rc;
+  if ((rc = M->d_f.alloc((size_t)M->n_inst))) return rc;
+  if ((rc = M->d_theta.alloc((size_t)std::max(P, 1)))) return rc;
+  return PSY_OK;
+}
+
+int psy_fit(psy_model* M, const double* theta, int skip_update, double* m2ll, double* latent_cm, double* pred_cm) {
+  if (!M || !m2ll || (M->P > 0 && !theta)) return fail(PSY_ERR_ARG, "psy_fit: bad arguments");
+  if (!M->d_tidx.p) return fail(PSY_ERR_STATE, "psy_fit: call psy_upload and psy_set_slots first");
+  if (!M->sr) return fail(PSY_ERR_STATE, "this module was loaded for srUpdate=TRUE only");
+  int rc;
+  if (M->P > 0) CU_TRY(cudaMemcpy(M->d_theta.p, theta, sizeof(double) * M->P, cudaMemcpyHostToDevice));
+  double *dl = nullptr, *dp = nullptr;
+  if (latent_cm) { if ((rc = M->d_latent.alloc((size_t)M->rows * M->n * 2))) return rc; dl = M->d_latent.p; }
+  if (pred_cm) { if ((rc = M->d_pred.alloc((size_t)M->rows * M->m * 2))) return rc; dp = M->d_pred.p; }
+  // base instances only; results land in d_f[0..N)
+  if ((rc = launch_filter(M, M->d_inst_base.p, nullptr, M->N, 0.0, skip_update, dl, dp))) return rc;
+  CU_TRY(cudaMemcpy(m2ll, M->d_f.p, sizeof(double) * M->N, cudaMemcpyDeviceToHost));
+  if (latent_cm) {
+    const long long tot = (long long)M->rows * M->n;
+    psy_to_colmajor<<<(unsigned)((tot + 255) / 256), 256>>>(dl, dl + tot, M->rows, M->n);
+    g_launches++;
+    CU_TRY(cudaMemcpy(latent_cm, dl + tot, sizeof(double) * tot, cudaMemcpyDeviceToHost));
+  }
+  if (pred_cm) {
+    const long long tot = (long long)M->rows * M->m;
+    psy_to_colmajor<<<(unsigned)((tot + 255) / 256), 256>>>(dp, dp + tot, M->rows, M->m);
+    g_launches++;
+    CU_TRY(cudaMemcpy(pred_cm, dp + tot, sizeof(double) * tot, cudaMemcpyDeviceToHost));
+  }
+  return PSY_OK;
+}
+
+int64_t psy_partial_len(const psy_model* M) { return M ? 5 * (int64_t)M->P + 2 : 0; }
+int64_t psy_n_instances(const psy_model* M) { return M ? M->n_inst : 0; }
+
+int psy_grad_level(psy_model* M, const double* theta, double eps, int direction, const unsigned char* need, void** partial_device) {
+  if (!M || (M->P > 0 && !theta)) return fail(PSY_ERR_ARG, "psy_grad_level: bad arguments");
+  if (direction < 0 || direction > 2) return fail(PSY_ERR_ARG, "Unknown direction argument. Possible are central, left and right");
+  if (!M->d_tidx.p) return fail(PSY_ERR_STATE, "psy_grad_level: call psy_upload and psy_set_slots first");
+  if (!M->sr) return fail(PSY_ERR_STATE, "this module was loaded for srUpdate=TRUE only");
+  int rc;
+  if (M->P > 0) CU_TRY(cudaMemcpy(M->d_theta.p, theta, sizeof(double) * M->P, cudaMemcpyHostToDevice));
+  const bool all = (direction == PSY_DIR_CENTRAL) && !need;
+  if (all) {
+    if ((rc = launch_filter(M, M->d_inst.p, nullptr, M->n_inst, eps, 0, nullptr, nullptr))) return rc;
+  } else {
+    // restricted sweep (one-sided direction, or the eps[] fallback for the sides that failed): build the sub-list
+    std::vector<PsyInst> sub;
+    std::vector<int> oidx;
+    const bool with_base = !need;  // the first level of a one-sided sweep also needs f0
+    for (int p = 0; p < M->N; p++) {
+      const int64_t o = M->h_inst_off[p];
+      if (with_base) { sub.push_back(PsyInst{p, -1}); oidx.push_back((int)o); }
+      int64_t j = 0;
+      for (int64_t q = M->h_dl_off[p]; q < M->h_dl_off[p + 1]; q++, j++) {
+        const int t = M->h_dl[q];
+        for (int side = 0; side < 2; side++) {
+          bool want = need ? need[2 * t + side] != 0
+                           : (direction == PSY_DIR_CENTRAL || (direction == PSY_DIR_LEFT && side == 0) || (direction == PSY_DIR_RIGHT && side == 1));
+          if (!want) continue;
+          sub.push_back(PsyInst{p, (t << 1) | side});
+          oidx.push_back((int)(o + 1 + 2 * j + side));
+        }
+      }
+    }
+    if ((rc = M->d_inst_sub.upload(sub.data(), sub.size()))) return rc;
+    if ((rc = M->d_out_idx.upload(oidx.data(), oidx.size()))) return rc;
+    if (!need) CU_TRY(cudaMemset(M->d_f.p, 0, sizeof(double) * M->n_inst));  // unused sides read as 0 (never consumed)
+    if ((rc = launch_filter(M, M->d_inst_sub.p, M->d_out_idx.p, (int64_t)sub.size(), eps, 0, nullptr, nullptr))) return rc;
+  }
+  if ((rc = run_reduction(M))) return rc;
+  if (partial_device) *partial_device = M->d_partial.p;
+  return PSY_OK;
+}
+
+int psy_grad_resolve(psy_model* M, const double* part, double eps, int level, int n_eps, int direction, unsigned char* need, int* done) {
+  if (!M || !part || !need || !done) return fail(PSY_ERR_ARG, "psy_grad_resolve: bad arguments");
+  const int P = M->P;
+  if (level == 0) {
+    M->base_total = part[0];
+    M->base_nonfinite = part[1];
+    M->Dval.assign((size_t)P * 2, 0.0);
+    M->eps_used.assign(P, 0.0);
+    M->resolved.assign((size_t)P * 2, 0);
+    if (M->wanted.size() != (size_t)P * 2) {
+      M->wanted.assign((size_t)P * 2, 0);
+      for (int t = 0; t < P; t++) {
+        M->wanted[2 * t + 0] = (direction == PSY_DIR_CENTRAL || direction == PSY_DIR_LEFT);
+        M->wanted[2 * t + 1] = (direction == PSY_DIR_CENTRAL || direction == PSY_DIR_RIGHT);
+      }
+    }
+  }
+  const double* Dp = part + 2;
+  const double* Dm = part + 2 + (size_t)P;
+  const double* nfp = part + 2 + 2 * (size_t)P;
+  const double* nfm = part + 2 + 3 * (size_t)P;
+  const double* nbt = part + 2 + 4 * (size_t)P;
+  int pending = 0;
+  for (int t = 0; t < P; t++) {
+    for (int side = 0; side < 2; side++) {
+      const size_t k = 2 * (size_t)t + side;
+      need[k] = 0;
+      if (!M->wanted[k] || M->resolved[k]) continue;
+      const double D = side ? Dp[t] : Dm[t];
+      const double nf = side ? nfp[t] : nfm[t];
+      // Σ -2LL over ALL persons is finite  <=>  untouched persons finite at base, touched persons finite here
+      const bool ok = (M->base_nonfinite - nbt[t] == 0.0) && nf == 0.0 && std::isfinite(D);
+      if (ok) {
+        M->resolved[k] = 1;
+        M->Dval[k] = D;
+        M->eps_used[t] += eps;  // R/modelTemplate.R:893, 914
+      } else if (level + 1 < n_eps) {
+        need[k] = 1;
+        pending++;
+      }
+    }
+  }
+  *done = (pending == 0);
+  return PSY_OK;
+}
+
+int psy_grad_finish(psy_model* M, int direction, double* grad, double* total) {
+  if (!M || !grad) return fail(PSY_ERR_ARG, "psy_grad_finish: bad arguments");
+  const double nan = std::nan("");
+  for (int t = 0; t < M->P; t++) {
+    const bool wl = M->wanted[2 * t], wr = M->wanted[2 * t + 1];
+    if ((wl && !M->resolved[2 * t]) || (wr && !M->resolved[2 * t + 1]) || (!wl && !wr)) { grad[t] = nan; continue; }
+    if (!(wl && wr) && M->base_nonfinite != 0.0) { grad[t] = nan; continue; }  // one-sided: the other side is Σ f0
+    const double dplus = wr ? M->Dval[2 * t + 1] : 0.0, dminus = wl ? M->Dval[2 * t] : 0.0;
+    grad[t] = (dplus - dminus) / M->eps_used[t];  // R/modelTemplate.R:926
+  }
+  if (total) *total = M->base_total;
+  M->wanted.clear();
+  return PSY_OK;
+}
+
+static int grad_sweep(psy_model* M, const double* theta, const double* eps, int n_eps, int direction, double* grad, double* total) {
+  if (!M || !eps || n_eps < 1 || !grad) return fail(PSY_ERR_ARG, "psy_gradients: bad arguments");
+  if (direction < 0 || direction > 2) return fail(PSY_ERR_ARG, "Unknown direction argument. Possible are central, left and right");
+  const int P = M->P;
+  std::vector<unsigned char> need((size_t)P * 2 + 1, 0);
+  std::vector<double> part((size_t)psy_partial_len(M));
+  M->wanted.clear();
+  int done = 0, rc;
+  for (int level = 0; level < n_eps && !done; level++) {
+    void* dptr = nullptr;
+    if ((rc = psy_grad_level(M, theta, eps[level], direction, (level == 0) ? nullptr : need.data(), &dptr))) return rc;
+    CU_TRY(cudaMemcpy(part.data(), dptr, sizeof(double) * part.size(), cudaMemcpyDeviceToHost));
+    if ((rc = psy_grad_resolve(M, part.data(), eps[level], level, n_eps, direction, need.data(), &done))) return rc;
+  }
+  return psy_grad_finish(M, direction, grad, total);
+}
+
+int psy_gradients(psy_model* M, const double* theta, const double* eps, int n_eps, int direction, double* grad, double* total) {
+  return grad_sweep(M, theta, eps, n_eps, direction, grad, total);
+}
+
+int psy_gradient(psy_model* M, const double* theta, int par, const double* eps, int n_eps, int direction, double* grad) {
+  if (!M || par < 0 || par >= M->P) return fail(PSY_ERR_ARG, "psy_gradient: parameter index out of range");
+  // the full sweep is one launch; a single parameter is a view of it (getGradient is what the reference's PSOCK
+  // workers call once per parameter, R/prepareModel.R:611-613 — here every "worker" reads the same batched result)
+  std::vector<double> g(M->P);
+  int rc = grad_sweep(M, theta, eps, n_eps, direction, g.data(), nullptr);
+  if (rc) return rc;
+  *grad = g[par];
+  return PSY_OK;
+}
+
+double psy_last_kernel_ms(const psy_model* M) { return M ? M->last_ms : 0.0; }
+int64_t psy_last_kernel_instances(const psy_model* M) { return M ? M->last_instances : 0; }
+int64_t psy_launch_count(void) { return g_launches; }
+void psy_counters_reset(void) { g_launches = 0; }
+
+int psy_measure_fp64_peak(double* tflops) {
+  if (!tflops) return fail(PSY_ERR_ARG, "psy_measure_fp64_peak: null argument");
+  int rc = load_driver();
+  if (rc) return rc;
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, 0));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+  double* out = nullptr;
+  CU_TRY(cudaMalloc((void**)&out, sizeof(double) * blocks * threads));
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(a, 0);
+    psy_dfma_peak<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
+    cudaEventRecord(b, 0);
+    g_launches++;
+    CU_TRY(cudaEventSynchronize(b));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    const double fl = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(out);
+  *tflops = best;
+  return PSY_OK;
+}
+
+int psy_kernel_info(const psy_model* M, int* regs, int* local_bytes, int* max_threads) {
+  if (!M || !M->fn) return fail(PSY_ERR_STATE, "psy_kernel_info: no module loaded");
+  int v = 0;
+  if (regs) { g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_NUM_REGS, M->fn); *regs = v; }
+  if (local_bytes) { g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, M->fn); *local_bytes = v; }
+  if (max_threads) { g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_MAX_THREADS_PER_BLOCK, M->fn); *max_threads = v; }
+  return PSY_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,517 @@
+"""Host-side mirror of psydiff's model object and R-facing API for the SR-UKF likelihood / gradient path.
+
+Same names, argument meaning and error behaviour as the reference (R/prepareModel.R, R/modelTemplate.R,
+src/exposeInlineFunctions.cpp); R lists become dicts, named numeric vectors become ordered dicts, matrices are
+numpy arrays.  All numerics happen in the CUDA kernel behind the C ABI (``_lib``) — this module only parses,
+builds the integer slot map that replaces the string-keyed parameterTable, and moves buffers.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+import re
+import warnings
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib, codegen
+from ._lib import PsydiffError
+
+_PERSON_WORDS = ("person", "persons", "individual", "individuals")  # R/prepareModel.R:717
+
+
+def _rnum(v) -> str:
+    """paste0()-style rendering of a number inside a label (R/prepareModel.R:719, 728)."""
+    fv = float(v)
+    return str(int(fv)) if fv == int(fv) else repr(fv)
+
+
+def checkEquation(equation: str):
+    """R/prepareModel.R:618-622."""
+    if ";" not in equation:
+        raise PsydiffError(f"Expected each command in ...\n{equation}\n to end with ; ")
+
+
+def _parse_element(el):
+    """One matrix element: a number, a numeric string, or "label = value" (R/prepareModel.R:641-654)."""
+    if isinstance(el, (int, float, np.integer, np.floating)):
+        return "", float(el)
+    s = str(el)
+    if "=" in s:
+        lab, val = s.split("=", 1)
+        return lab.replace(" ", ""), float(val)
+    return "", float(s)
+
+
+def sepNameFromValue(mat):
+    """R/prepareModel.R:800-818: split a (character or numeric) matrix into labels and values."""
+    arr = np.asarray(mat, dtype=object)
+    if arr.ndim == 0:
+        arr = arr.reshape(1, 1)
+    if arr.ndim == 1:
+        arr = arr.reshape(-1, 1)
+    labels = np.full(arr.shape, "", dtype=object)
+    values = np.zeros(arr.shape, dtype=float)
+    for i in range(arr.shape[0]):
+        for j in range(arr.shape[1]):
+            labels[i, j], values[i, j] = _parse_element(arr[i, j])
+    return {"labels": labels, "values": values}
+
+
+def sdeModelMatrix(values, labels):
+    """R/prepareModel.R:783-798: combine numeric values and labels into a "label = value" character matrix."""
+    values = np.asarray(values, dtype=float)
+    labels = np.asarray(labels, dtype=object)
+    if values.shape != labels.shape:
+        raise PsydiffError("values and labels have different dimensions")
+    out = np.empty(values.shape, dtype=object)
+    for i in range(values.shape[0]):
+        for j in range(values.shape[1]):
+            lab = labels[i, j]
+            empty = lab is None or lab == "" or (isinstance(lab, float) and np.isnan(lab))
+            out[i, j] = repr(float(values[i, j])) if empty else f"{lab} = {float(values[i, j])!r}"
+    return out
+
+
+def chol2LogChol(matValues, matLabels, sanityChecks=True, matrixName=""):
+    """R/prepareModel.R:820-842: log-Cholesky parameterisation; diagonal labels get the prefix "ln"."""
+    vals = np.array(matValues, dtype=float)
+    labs = np.array(matLabels, dtype=object)
+    d = np.diag_indices(vals.shape[0])
+    if sanityChecks and np.any(np.abs(vals[d]) < .01):
+        warnings.warn(f"Setting the diagonal elements of {matrixName} to very small values will often result in errors. "
+                      "The small values will be replaced by .01. Set sanityChecks = FALSE to prevent this.")
+        dv = vals[d]
+        dv[np.abs(dv) < .01] = .01
+        vals[d] = dv
+    with np.errstate(divide="ignore", invalid="ignore"):
+        vals[d] = np.log(vals[d])
+    out = np.empty(vals.shape, dtype=object)
+    for i in range(vals.shape[0]):
+        for j in range(vals.shape[1]):
+            lab = labs[i, j]
+            if i == j and lab != "":
+                lab = "ln" + lab
+            out[i, j] = repr(float(vals[i, j])) if lab == "" else f"{lab} = {float(vals[i, j])!r}"
+    return out
+
+
+class Container:
+    """One entry of model$pars$parameterList: a scalar ("double") or a matrix, with the free-slot id of every element."""
+
+    def __init__(self, name, kind, values, slots):
+        self.name, self.kind, self.values, self.slots = name, kind, values, slots  # values/slots: 2-D arrays
+
+    @property
+    def shape(self):
+        return self.values.shape
+
+
+def extractParameters(elementNames: Sequence[str], parameters: Dict[str, object]):
+    """R/prepareModel.R:624-702.  Returns (containers, slot table rows, startValues)."""
+    containers: List[Container] = []
+    rows = []  # dicts: label, value, target, targetClass, row, col
+    start = {}
+    for name in elementNames:
+        cur = parameters[name]
+        if isinstance(cur, (int, float, np.integer, np.floating)):
+            slot = len(rows)
+            rows.append(dict(label=name, value=float(cur), target=name, targetClass="double", row=0, col=0))
+            containers.append(Container(name, "double", np.array([[float(cur)]]), np.array([[slot]])))
+            start[name] = float(cur)
+            continue
+        arr = np.asarray(cur, dtype=object)
+        if arr.ndim == 1:
+            # quirk Q5: the reference tags these "colvec", which setParameterList_C rejects
+            # (inst/include/psydiffBasic.h:102-111); vectors are treated as n x 1 matrices here.
+            arr = arr.reshape(-1, 1)
+        if arr.ndim != 2:
+            raise PsydiffError(f"Unknown data type for parameter {name}. Allowed are numeric, matrix, and vector.")
+        vals = np.zeros(arr.shape, dtype=float)
+        slots = np.full(arr.shape, -1, dtype=np.int64)
+        for ro in range(arr.shape[0]):
+            for co in range(arr.shape[1]):
+                lab, v = _parse_element(arr[ro, co])
+                vals[ro, co] = v
+                if lab != "":
+                    slots[ro, co] = len(rows)
+                    rows.append(dict(label=lab, value=v, target=name, targetClass="matrix", row=ro, col=co))
+        containers.append(Container(name, "matrix", vals, slots))
+        start[name] = vals.copy()
+    return containers, rows, start
+
+
+class ParameterTable:
+    """model$pars$parameterTable (R/prepareModel.R:471-476) without materialising N x F rows of strings.
+
+    The reference replicates the F slot rows once per person and relabels grouped parameters; everything the hot
+    path needs from that table is ``theta_index[N, F]`` (slot -> position of its label among the unique labels).
+    The R-visible columns are available as properties for small models.
+    """
+
+    def __init__(self, slot_rows, persons, theta_labels, theta_values, theta_index):
+        self.slot_rows = slot_rows
+        self.persons = np.asarray(persons)
+        self.theta_labels: List[str] = list(theta_labels)
+        self.theta_values = np.asarray(theta_values, dtype=float).copy()
+        self.theta_index = np.ascontiguousarray(theta_index, dtype=np.int32)  # N x F
+        self.changed = np.ones(self.theta_index.shape, dtype=bool)
+        self._label_pos = {l: i for i, l in enumerate(self.theta_labels)}
+
+    # R-visible columns (person-major, slot-minor), materialised on demand
+    @property
+    def label(self):
+        tl = np.asarray(self.theta_labels, dtype=object)
+        return tl[self.theta_index.reshape(-1)]
+
+    @property
+    def value(self):
+        return self.theta_values[self.theta_index.reshape(-1)]
+
+    @property
+    def person(self):
+        return np.repeat(self.persons, self.theta_index.shape[1])
+
+    @property
+    def target(self):
+        return np.tile(np.asarray([r["target"] for r in self.slot_rows], dtype=object), len(self.persons))
+
+    def __len__(self):
+        return self.theta_index.size
+
+    def copy(self):
+        c = ParameterTable(self.slot_rows, self.persons, self.theta_labels, self.theta_values, self.theta_index)
+        c.changed = self.changed.copy()
+        return c
+
+
+def makeGroups(grouping, groupingvariables, slot_rows, persons_unique):
+    """R/prepareModel.R:704-734 → per-person labels → (theta_labels, theta_values, theta_index[N,F]).
+
+    "par | person;" gives label par_p<id>; "par | g;" gives par_p<groupingvariables$g[id]> (R indexes the grouping
+    vector by the person id, 1-based).  theta is ordered by first appearance in the person-major table.
+    """
+    N, F = len(persons_unique), len(slot_rows)
+    slot_labels = [r["label"] for r in slot_rows]
+    group_of: Dict[str, str] = {}
+    if grouping is not None:
+        checkEquation(grouping)
+        g = grouping.replace("\n", "").replace(" ", "")
+        for grp in [s for s in g.split(";") if s != ""]:
+            parts = grp.split("|")
+            if len(parts) < 2:
+                raise PsydiffError(f"Cannot parse grouping statement {grp}")
+            if parts[1] not in _PERSON_WORDS:
+                if groupingvariables is None or parts[1] not in groupingvariables:
+                    raise PsydiffError(f"Grouping variable {parts[1]} not found in groupingvariables")
+            group_of[parts[0]] = parts[1]
+    # label ids per (person, slot)
+    labels: List[str] = []
+    pos: Dict[str, int] = {}
+    lab_idx = np.empty((N, F), dtype=np.int64)
+    for k, lab in enumerate(slot_labels):
+        if lab not in group_of:
+            if lab not in pos:
+                pos[lab] = len(labels)
+                labels.append(lab)
+            lab_idx[:, k] = pos[lab]
+            continue
+        gv = group_of[lab]
+        if gv in _PERSON_WORDS:
+            keys = np.asarray(persons_unique, dtype=float)
+        else:
+            gvar = groupingvariables[gv]
+            if isinstance(gvar, dict):
+                keys = np.asarray([gvar[p] for p in persons_unique], dtype=float)
+            else:
+                gvar = np.asarray(gvar, dtype=float)
+                keys = gvar[np.asarray(persons_unique, dtype=np.int64) - 1]  # R: groupingIndicator[p]
+        uk, inv = np.unique(keys, return_inverse=True)
+        ids = np.empty(len(uk), dtype=np.int64)
+        for u, kv in enumerate(uk):
+            l2 = f"{lab}_p{_rnum(kv)}"
+            if l2 not in pos:
+                pos[l2] = len(labels)
+                labels.append(l2)
+            ids[u] = pos[l2]
+        lab_idx[:, k] = ids[inv]
+    # order theta by first appearance (person-major, slot-minor)
+    flat = lab_idx.reshape(-1)
+    first = np.full(len(labels), flat.size, dtype=np.int64)
+    np.minimum.at(first, flat, np.arange(flat.size, dtype=np.int64))
+    order = np.argsort(first, kind="stable")
+    rank = np.empty(len(labels), dtype=np.int64)
+    rank[order] = np.arange(len(labels))
+    theta_index = rank[lab_idx].astype(np.int32)
+    theta_labels = [labels[i] for i in order]
+    slot_vals = np.asarray([r["value"] for r in slot_rows], dtype=float)
+    theta_values = np.zeros(len(labels))
+    # value of a label = value of its first row (getParameterValues_C, inst/include/psydiffBasic.h:47-54)
+    fpos = first[order]
+    theta_values[:] = slot_vals[fpos % max(F, 1)] if F > 0 else 0.0
+    return theta_labels, theta_values, theta_index
+
+
+class PsydiffModel(dict):
+    """The psydiffModel list of R/prepareModel.R:518-540 (a dict with the same field names)."""
+
+    def __deepcopy__(self, memo):
+        new = PsydiffModel()
+        for k, v in self.items():
+            if k in ("_handle",):
+                new[k] = v  # device handle and resident dataset are shared by clones (they are immutable)
+            elif k == "data":
+                new[k] = v  # the dataset is never mutated
+            else:
+                new[k] = copy.deepcopy(v, memo)
+        return new
+
+
+def newPsydiff(dataset, latentEquations, manifestEquations, L, Rchol, A0, m0, grouping=None, parameters=None,
+               groupingvariables=None, additional=None, srUpdate=True, alpha=.2, beta=2.0, kappa=0.0, timeStep=None,
+               integrateFunction="default", breakEarly=True, verbose=0, eps=(1e-8, 1e-6, 1e-5, 1e-4),
+               direction="central", sanityChecks=True) -> PsydiffModel:
+    """newPsydiff (R/prepareModel.R:399-545): validate, build the log-Cholesky containers and the parameter table,
+    splice the user's equations into the kernel template.  ``model["cppCode"]`` holds the CUDA translation unit."""
+    A0s, Ls, Rs = sepNameFromValue(A0), sepNameFromValue(L), sepNameFromValue(Rchol)
+    nlatent, nmanifest = Ls["values"].shape[1], Rs["values"].shape[1]
+    checkEquation(latentEquations)
+    checkEquation(manifestEquations)
+    if not isinstance(dataset, dict):
+        raise PsydiffError("dataset must be a list")
+    for nm in dataset:
+        if nm not in ("person", "observations", "dt"):
+            raise PsydiffError("Unknown field in dataset. Dataset must have the fields 'person',\n           'observations', 'dt'")
+    obs = np.asarray(dataset["observations"], dtype=float)
+    if obs.ndim != 2:
+        raise PsydiffError("Field observations in dataset has to be of type matrix")
+    if obs.shape[1] != nmanifest:
+        raise PsydiffError("Dataset and R differ in their number of manifest variables.")
+    if parameters is None or not isinstance(parameters, dict):
+        raise PsydiffError("parameters must be of class data.frame")
+    if not (additional is None or isinstance(additional, dict)):
+        raise PsydiffError("additional must be of class data.frame or NULL")
+    dt = np.asarray(dataset["dt"], dtype=float).reshape(-1)
+    persons = np.asarray(dataset["person"]).reshape(-1)
+    if len(dt) != obs.shape[0] or len(persons) != obs.shape[0]:
+        raise PsydiffError("person, observations and dt must have the same number of rows")
+    if timeStep is None:  # R/prepareModel.R:435-438
+        mn = np.min(dt[dt > 0])
+        timeStep = np.linspace(mn / 30, mn / 10, 5)
+    timeStep = np.atleast_1d(np.asarray(timeStep, dtype=float))
+
+    A0LogChol = chol2LogChol(A0s["values"], A0s["labels"], sanityChecks, "A0")
+    LLogChol = chol2LogChol(Ls["values"], Ls["labels"], sanityChecks, "L")
+    RLogChol = chol2LogChol(Rs["values"], Rs["labels"], sanityChecks, "Rchol")
+    parameters = dict(parameters)
+    parameters["A0LogChol"] = A0LogChol
+    parameters["LLogChol"] = LLogChol
+    parameters["RLogChol"] = RLogChol
+    parameters["m0"] = m0
+    containers, slot_rows, startValues = extractParameters(list(parameters.keys()), parameters)
+
+    # persons: contiguous row blocks (the reference writes to min(rowInd)+timePoint, R/modelTemplate.R:361)
+    change = np.flatnonzero(persons[1:] != persons[:-1]) + 1
+    row_off = np.concatenate([[0], change, [len(persons)]]).astype(np.int64)
+    persons_unique = persons[row_off[:-1]]
+    if len(np.unique(persons_unique)) != len(persons_unique):
+        raise PsydiffError("rows of one person must be contiguous in the dataset")
+    theta_labels, theta_values, theta_index = makeGroups(grouping, groupingvariables, slot_rows, persons_unique)
+    ptab = ParameterTable(slot_rows, persons_unique, theta_labels, theta_values, theta_index)
+
+    spec = codegen.ModelSpec(nlatent=nlatent, nmanifest=nmanifest, containers=containers, n_slots=len(slot_rows),
+                             latentEquations=latentEquations, manifestEquations=manifestEquations, srUpdate=bool(srUpdate))
+    cuda_src = codegen.emit_cuda(spec)
+
+    model = PsydiffModel(
+        pars={"parameterList": startValues, "parameterTable": ptab},
+        nlatent=nlatent, nmanifest=nmanifest,
+        data={"person": persons, "observations": obs, "dt": dt},
+        additional=additional,
+        m2LL=np.zeros(len(persons_unique)),
+        predictedManifest=np.full((obs.shape[0], nmanifest), -99999.99),
+        latentScores=np.full((obs.shape[0], nlatent), -99999.99),
+        alpha=float(alpha), beta=float(beta), kappa=float(kappa), timeStep=timeStep,
+        integrateFunction=integrateFunction, breakEarly=bool(breakEarly), verbose=verbose,
+        eps=np.atleast_1d(np.asarray(eps, dtype=float)), direction=direction, srUpdate=bool(srUpdate),
+        cppCode=cuda_src,
+    )
+    model["_spec"] = spec
+    model["_row_off"] = row_off
+    model["_persons_unique"] = persons_unique
+    model["_handle"] = None
+    return model
+
+
+class _Handle:
+    """Owns the psy_model* and the HBM-resident dataset; shared by clones of the model object."""
+
+    def __init__(self, ptr, cubin):
+        self.ptr, self.cubin = ptr, cubin
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib().psy_model_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def compileModelSource(psydiffModel, extra_flags: str = "") -> str:
+    """Compile the model's CUDA TU to a cubin for sm_100a (no GPU needed).  Returns the cubin path."""
+    L = _lib.lib()
+    buf = C.create_string_buffer(4096)
+    _lib.check(L.psy_model_compile(psydiffModel["cppCode"].encode(), _lib.CSRC_DIR.encode(), _lib.CACHE_DIR.encode(),
+                                   extra_flags.encode(), buf, 4096))
+    return buf.value.decode()
+
+
+def compileModel(psydiffModel, extra_flags: str = ""):
+    """compileModel (R/prepareModel.R:553-562): compile the model for sm_100a, load it and make the dataset resident
+    on the current device.  Afterwards fitModel / getGradients / getGradient work on this model object."""
+    L = _lib.lib()
+    cubin = compileModelSource(psydiffModel, extra_flags)
+    spec = psydiffModel["_spec"]
+    ptr = L.psy_model_create(spec.nlatent, spec.nmanifest, spec.n_slots, cubin.encode())
+    if not ptr:
+        raise PsydiffError(L.psy_last_error().decode())
+    h = _Handle(ptr, cubin)
+    data = psydiffModel["data"]
+    obs_cm = np.asfortranarray(data["observations"], dtype=np.float64)
+    dt = np.ascontiguousarray(data["dt"], dtype=np.float64)
+    row_off = np.ascontiguousarray(psydiffModel["_row_off"], dtype=np.int64)
+    pid = np.ascontiguousarray(np.asarray(psydiffModel["_persons_unique"], dtype=np.float64).astype(np.int32))
+    _lib.check(L.psy_upload(ptr, obs_cm.shape[0], len(pid), obs_cm.ctypes.data_as(_lib.c_double_p), _lib.dptr(dt),
+                            _lib.i64ptr(row_off), _lib.iptr(pid)))
+    ptab = psydiffModel["pars"]["parameterTable"]
+    tidx = np.ascontiguousarray(ptab.theta_index, dtype=np.int32)
+    _lib.check(L.psy_set_slots(ptr, len(ptab.theta_labels), _lib.iptr(tidx)))
+    psydiffModel["_handle"] = h
+    return psydiffModel
+
+
+_STEPPERS = {"rk4": 0, "runge_kutta_dopri5": 1}
+
+
+def _push_settings(model):
+    h = model.get("_handle")
+    if h is None or not h.ptr:
+        raise PsydiffError("model is not compiled: call compileModel(model) first")
+    ts = np.ascontiguousarray(model["timeStep"], dtype=np.float64)
+    stepper = _STEPPERS.get(model["integrateFunction"], 2)  # anything else is the "default" branch (R/modelTemplate.R:334)
+    _lib.check(_lib.lib().psy_model_settings(h.ptr, float(model["alpha"]), float(model["beta"]), float(model["kappa"]),
+                                             stepper, _lib.dptr(ts), len(ts), 1 if model.get("srUpdate", True) else 0))
+    return h
+
+
+def getParameterValues(psydiffModel) -> Dict[str, float]:
+    """getParameterValues (inst/include/psydiffBasic.h:36-58): unique label -> value (first-appearance order, quirk Q6)."""
+    pt = psydiffModel["pars"]["parameterTable"]
+    return {l: float(v) for l, v in zip(pt.theta_labels, pt.theta_values)}
+
+
+def setParameterValues(parameterTable: ParameterTable, parameterValues, parameterLabels=None):
+    """setParameterValues (inst/include/psydiffBasic.h:4-33): write values by label, flag changed rows; mutates the table."""
+    if parameterLabels is None and isinstance(parameterValues, dict):
+        parameterLabels = list(parameterValues.keys())
+        parameterValues = list(parameterValues.values())
+    parameterValues = np.atleast_1d(np.asarray(parameterValues, dtype=float))
+    if len(parameterValues) != len(parameterLabels):
+        raise PsydiffError("Length of parameterValues and parameterLabels does not match")
+    for v, lab in zip(parameterValues, parameterLabels):
+        i = parameterTable._label_pos.get(lab)
+        if i is None:
+            warnings.warn("The following parameter was not found in the parameterTable: " + str(lab))
+            continue
+        if parameterTable.theta_values[i] != v:
+            parameterTable.theta_values[i] = v
+            parameterTable.changed[parameterTable.theta_index == i] = True
+
+
+def clonePsydiffModel(model):
+    """clonePsydiffModel (src/exposeInlineFunctions.cpp:305-308): deep copy; the device-resident dataset is shared."""
+    return copy.deepcopy(model)
+
+
+def fitModel(psydiffModel, skipUpdate: bool = False):
+    """fitModel (R/modelTemplate.R:165-420): per-person -2LL, latentScores, predictedManifest.
+
+    Like the reference it overwrites model$m2LL / $latentScores / $predictedManifest in place and clears the
+    ``changed`` flags (R/modelTemplate.R:410-414).  Every person is evaluated on every call (stateless parameter
+    semantics, quirk Q4); a person whose filter fails numerically gets NaN (quirk Q2)."""
+    h = _push_settings(psydiffModel)
+    pt = psydiffModel["pars"]["parameterTable"]
+    theta = np.ascontiguousarray(pt.theta_values, dtype=np.float64)
+    N = pt.theta_index.shape[0]
+    rows = psydiffModel["data"]["observations"].shape[0]
+    m2ll = np.empty(N)
+    lat = np.empty((rows, psydiffModel["nlatent"]), order="F")
+    pred = np.empty((rows, psydiffModel["nmanifest"]), order="F")
+    _lib.check(_lib.lib().psy_fit(h.ptr, _lib.dptr(theta) if len(theta) else None, 1 if skipUpdate else 0, _lib.dptr(m2ll),
+                                  lat.ctypes.data_as(_lib.c_double_p), pred.ctypes.data_as(_lib.c_double_p)))
+    psydiffModel["m2LL"] = m2ll
+    psydiffModel["latentScores"] = lat
+    psydiffModel["predictedManifest"] = pred
+    pt.changed[:] = False
+    return {"latentScores": lat, "predictedManifest": pred, "m2LL": m2ll}
+
+
+_DIRS = {"central": 0, "left": 1, "right": 2}
+
+
+def _direction(model):
+    d = model["direction"]
+    if d not in _DIRS:
+        raise PsydiffError("Unknown direction argument. Possible are central, left and right")  # R/modelTemplate.R:868-870
+    return _DIRS[d]
+
+
+def getGradients(psydiffModel) -> Dict[str, float]:
+    """getGradients (R/modelTemplate.R:852-930): finite-difference gradient of Σ -2LL for every parameter, with the
+    eps[] fallback; all 2P+1 filter sweeps run as one batched launch per eps level.  The model is not modified."""
+    h = _push_settings(psydiffModel)
+    pt = psydiffModel["pars"]["parameterTable"]
+    theta = np.ascontiguousarray(pt.theta_values, dtype=np.float64)
+    eps = np.ascontiguousarray(psydiffModel["eps"], dtype=np.float64)
+    g = np.empty(len(theta))
+    tot = C.c_double(0.0)
+    _lib.check(_lib.lib().psy_gradients(h.ptr, _lib.dptr(theta), _lib.dptr(eps), len(eps), _direction(psydiffModel),
+                                        _lib.dptr(g), C.byref(tot)))
+    return {l: float(v) for l, v in zip(pt.theta_labels, g)}
+
+
+def getGradient(psydiffModel, currentParameterValues, par: int) -> Dict[str, float]:
+    """getGradient (R/modelTemplate.R:932-1008): gradient for the single 0-based parameter ``par`` at the given values."""
+    h = _push_settings(psydiffModel)
+    pt = psydiffModel["pars"]["parameterTable"]
+    if isinstance(currentParameterValues, dict):
+        theta = np.array([currentParameterValues[l] for l in pt.theta_labels], dtype=np.float64)
+    else:
+        theta = np.ascontiguousarray(currentParameterValues, dtype=np.float64)
+    eps = np.ascontiguousarray(psydiffModel["eps"], dtype=np.float64)
+    g = C.c_double(0.0)
+    _lib.check(_lib.lib().psy_gradient(h.ptr, _lib.dptr(theta), int(par), _lib.dptr(eps), len(eps), _direction(psydiffModel),
+                                       C.byref(g)))
+    return {pt.theta_labels[par]: g.value}
+
+
+def compileParallelGradients(psydiffModel, nCores: int = 1):
+    """compileParallelGradients (R/prepareModel.R:572-589).  The reference starts nCores PSOCK workers that each
+    recompile the model; here the parameter sweep is already one batched GPU launch, so this only compiles the
+    model (if needed) and sets ``model["cl"]`` so callers that test it (R/optimWrapper.R:169-177) take the same route."""
+    if psydiffModel.get("_handle") is None:
+        compileModel(psydiffModel)
+    psydiffModel["cl"] = {"nCores": int(nCores), "backend": "cuda-batched"}
+    return psydiffModel
+
+
+def stopParallelGradients(psydiffModel):
+    """stopParallelGradients (R/prepareModel.R:598-600)."""
+    psydiffModel["cl"] = None
+
+
+def getGradientsParallel(psydiffModel) -> Dict[str, float]:
+    """getGradientsParallel (R/prepareModel.R:608-616): same result as getGradients, ordered by names(pars)."""
+    return getGradients(psydiffModel)

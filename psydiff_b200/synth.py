@@ -1,0 +1,141 @@
+"""Deterministic synthetic workloads for the configs of BASELINE.json: model definition + simulated data.
+
+Each ``config_cX`` returns the keyword arguments of ``newPsydiff`` (same argument names as R/prepareModel.R:399-406).
+Data are simulated from the model itself (there is no network for datasets); generators are seeded numpy PCG64.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _ou_discretise(A, Q, dt):
+    """Exact discretisation of dx = A x dt + G dW, G G' = Q (Van Loan): returns (Ad, Qd)."""
+    from scipy.linalg import expm
+    n = A.shape[0]
+    Mx = np.zeros((2 * n, 2 * n))
+    Mx[:n, :n] = -A
+    Mx[:n, n:] = Q
+    Mx[n:, n:] = A.T
+    E = expm(Mx * dt)
+    Ad = E[n:, n:].T
+    Qd = Ad @ E[:n, n:]
+    return Ad, (Qd + Qd.T) / 2
+
+
+def config_c1(N=20, T=50, seed=20210129, missing=0.0, **settings):
+    """C1/C2: the bivariate linear-drift (OU) example of R/prepareModel.R:36-118: dx = DRIFT*x; y = MANIFESTMEANS + LAMBDA*x;
+    11 free parameters (4 drift, 2 manifest means, 3 T0 log-Cholesky, 2 ln-diffusion)."""
+    rng = np.random.default_rng(seed)
+    DRIFT = np.array([[-.3, 0.0], [.2, -.5]])
+    Lc = np.diag([np.sqrt(.5)] * 2)
+    Rc = np.diag([np.sqrt(.5)] * 2)
+    m0 = np.array([1.0, 2.0])
+    Ad, Qd = _ou_discretise(DRIFT, Lc @ Lc.T, 1.0)
+    Lq = np.linalg.cholesky(Qd)
+    x = m0[None, :] + rng.standard_normal((N, 2))  # A0 = I
+    obs = np.empty((N, T, 2))
+    for t in range(T):
+        if t > 0:
+            x = x @ Ad.T + rng.standard_normal((N, 2)) @ Lq.T
+        obs[:, t, :] = x + rng.standard_normal((N, 2)) @ Rc.T
+    if missing > 0:
+        obs[rng.random(obs.shape) < missing] = np.nan
+    dt = np.tile(np.concatenate([[0.0], np.ones(T - 1)]), N)
+    dataset = {"person": np.repeat(np.arange(1, N + 1), T), "observations": obs.reshape(N * T, 2), "dt": dt}
+    parameters = {
+        "LAMBDA": np.array([["1", "0"], ["0", "1"]], dtype=object),
+        "DRIFT": np.array([["drift_eta1 = -0.3", "drift_eta1_eta2 = 0.0"],
+                           ["drift_eta2_eta1 = 0.2", "drift_eta2 = -0.5"]], dtype=object),
+        "MANIFESTMEANS": np.array([["mm_Y1 = 0.0"], ["mm_Y2 = 0.0"]], dtype=object),
+    }
+    kw = dict(
+        dataset=dataset,
+        latentEquations="dx = DRIFT*x;",
+        manifestEquations="y = MANIFESTMEANS + LAMBDA*x;",
+        L=np.array([[f"eta1_eta1 = {float(np.sqrt(.5))!r}", "0"], ["0", f"eta2_eta2 = {float(np.sqrt(.5))!r}"]], dtype=object),
+        Rchol=Rc,
+        A0=np.array([["T0var_eta1 = 1", "0"], ["T0var_eta2_eta1 = 0", "T0var_eta2 = 1"]], dtype=object),
+        m0=np.array([["1"], ["2"]], dtype=object),
+        parameters=parameters,
+        timeStep=np.array([1.0 / 30]), integrateFunction="rk4", eps=np.array([1e-6]), direction="central",
+    )
+    kw.update(settings)
+    return kw
+
+
+def config_c2(N=100_000, T=100, seed=20210130, **settings):
+    """C2: the C1 model at N=100k, T=100, 5 % of the observations missing at random, fixed-step RK4 h=1/30."""
+    return config_c1(N=N, T=T, seed=seed, missing=0.05, **settings)
+
+
+_C4_LATENT = """
+dx(0) = x(1);
+dx(1) = mu1*(1.0 - x(0)*x(0))*x(1) - om1*om1*x(0) + k12*(x(2) - x(0)) + k13*(x(4) - x(0));
+dx(2) = x(3);
+dx(3) = mu2*(1.0 - x(2)*x(2))*x(3) - om2*om2*x(2) + k21*(x(0) - x(2)) + k23*(x(4) - x(2));
+dx(4) = x(5);
+dx(5) = mu3*(1.0 - x(4)*x(4))*x(5) - om3*om3*x(4) + k31*(x(0) - x(4)) + k32*(x(2) - x(4));
+"""
+
+
+def _vdp3_drift(x, mu, om, k):
+    q, v = x[:, 0::2], x[:, 1::2]
+    dx = np.empty_like(x)
+    dx[:, 0::2] = v
+    coup = np.empty_like(q)
+    coup[:, 0] = k[0] * (q[:, 1] - q[:, 0]) + k[1] * (q[:, 2] - q[:, 0])
+    coup[:, 1] = k[2] * (q[:, 0] - q[:, 1]) + k[3] * (q[:, 2] - q[:, 1])
+    coup[:, 2] = k[4] * (q[:, 0] - q[:, 2]) + k[5] * (q[:, 1] - q[:, 2])
+    dx[:, 1::2] = mu * (1.0 - q * q) * v - (om * om)[None, :] * q + coup
+    return dx
+
+
+def config_c4(N=1_000_000, T=100, seed=20210132, n_groups=8, **settings):
+    """C4: three diffusively coupled Van der Pol oscillators (n = m = 6, y = x), irregular time intervals,
+    mu1..mu3 specific to 8 groups (P = 3*8 + 27 = 51 parameters, 30 per person -> 61 filter instances per person),
+    fixed-step RK4 with the package default h = min(dt>0)/30."""
+    rng = np.random.default_rng(seed)
+    group = (np.arange(N) % n_groups) + 1
+    mu_g = np.linspace(0.6, 1.4, n_groups)[:, None] * np.array([1.0, 0.9, 1.1])[None, :]   # [group, oscillator]
+    om = np.array([1.0, 1.2, 0.8])
+    kk = np.array([0.10, 0.05, 0.08, 0.12, 0.06, 0.09])
+    ldiff, rsd = 0.1, 0.3
+    m0 = np.array([1.0, 0.0, -0.5, 0.5, 0.3, -0.8])
+    dts = rng.choice([0.5, 0.75, 1.0, 1.25, 1.5], size=(N, T)) + rng.random((N, T)) * 0.1
+    dts[:, 0] = 0.0
+    obs = np.empty((N, T, 6))
+    CH = 65536
+    sub = 0.05
+    for c0 in range(0, N, CH):
+        c1 = min(N, c0 + CH)
+        nb = c1 - c0
+        mu = mu_g[group[c0:c1] - 1]
+        x = m0[None, :] + 0.5 * rng.standard_normal((nb, 6))
+        for t in range(T):
+            rem = dts[c0:c1, t].copy()
+            nsub = int(np.ceil(rem.max() / sub)) if t > 0 else 0
+            for _ in range(nsub):
+                h = np.minimum(rem, sub)
+                rem -= h
+                k1 = _vdp3_drift(x, mu, om, kk)
+                k2 = _vdp3_drift(x + h[:, None] * k1, mu, om, kk)
+                x = x + 0.5 * h[:, None] * (k1 + k2) + ldiff * np.sqrt(h)[:, None] * rng.standard_normal((nb, 6))
+            obs[c0:c1, t, :] = x + rsd * rng.standard_normal((nb, 6))
+    dataset = {"person": np.repeat(np.arange(1, N + 1), T), "observations": obs.reshape(N * T, 6), "dt": dts.reshape(-1)}
+    parameters = {"mu1": 1.0, "mu2": 0.9, "mu3": 1.1, "om1": 1.0, "om2": 1.2, "om3": 0.8,
+                  "k12": 0.10, "k13": 0.05, "k21": 0.08, "k23": 0.12, "k31": 0.06, "k32": 0.09}
+    Lm = np.full((6, 6), "0", dtype=object)
+    Rm = np.full((6, 6), "0", dtype=object)
+    for i in range(6):
+        Lm[i, i] = f"l{i + 1} = {ldiff}"
+        Rm[i, i] = f"r{i + 1} = {rsd}"
+    kw = dict(
+        dataset=dataset, latentEquations=_C4_LATENT, manifestEquations="y = x;",
+        L=Lm, Rchol=Rm, A0=np.eye(6) * 0.5,
+        m0=np.array([[f"m0_{i + 1} = {m0[i]}"] for i in range(6)], dtype=object),
+        parameters=parameters,
+        grouping="mu1 | grp; mu2 | grp; mu3 | grp;", groupingvariables={"grp": group.astype(float)},
+        integrateFunction="rk4", eps=np.array([1e-6]), direction="central",
+    )
+    kw.update(settings)
+    return kw
