@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py — SR-UKF person-timesteps/sec (−2LL + full central-FD gradient, FP64) on N B200 GPUs.
+
+One "step" = one evaluation of [Σ −2LL + full finite-difference gradient] of the C4 workload of BASELINE.json
+(6-latent coupled Van der Pol model, irregular time intervals, group-specific parameters, T = 100): every person's
+2·P_i + 1 = 61 filter instances run as ONE batched launch of the filter kernel, followed by the K3 reduction, the
+all-reduce of the partial sums (N > 1) and the D2H read of 1 + P doubles.
+
+Weak scaling: --persons-per-gpu persons on every GPU (default 125 000, the per-GPU shard of the N = 1M x 8-GPU config;
+8 GPUs reproduce C4 exactly).  Inputs (600 MB/GPU of observations) are larger than the 126 MB L2.
+
+    python bench.py --gpus 1 --steps 2 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P bench.py --gpus 8 ...
+    python bench.py --impl reference          # the CPU path (oracle port of the reference) on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SR-UKF person-timesteps/sec (-2LL + FD gradient, FP64)"
+UNIT = "person-timesteps/s"
+C4_FF, C4_FH = 39, 0   # flops of one drift / measurement evaluation of the C4 equations (counted from the model source)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--persons-per-gpu", type=int, default=125_000)
+    ap.add_argument("--timepoints", type=int, default=100)
+    ap.add_argument("--cpu-persons", type=int, default=0, help="persons in the CPU sample (0 = 2 per host core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_shard(args, rank):
+    import psydiff_b200 as pd
+    from psydiff_b200 import synth
+    npg = args.persons_per_gpu
+    kw = synth.config_c4(N=npg, T=args.timepoints, seed=20210132 + rank, id_offset=rank * npg)
+    return pd.newPsydiff(**kw)
+
+
+def cpu_sample(args, model, steps=1, warmup=0):
+    """Time the CPU path (oracle port of the reference algorithm, g++ -O2, no FMA contraction) on a bounded sample of
+    the same workload with all host threads; returns (person-timesteps/s, cores, description, seconds per step)."""
+    from oracle.oracle import Oracle
+    cores = os.cpu_count() or 1
+    n = args.cpu_persons or 2 * cores
+    n = min(n, model["pars"]["parameterTable"].theta_index.shape[0])
+    orc = Oracle(model)
+    persons = np.arange(n)
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.gradients(nthreads=cores, persons=persons)
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    sec = sum(ts) / len(ts)
+    T = args.timepoints
+    return n * T / sec, cores, (f"first {n} persons of the C4 shard x T={T}, -2LL + full central FD gradient "
+                                f"(61 filter sweeps/person), {cores} threads"), sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    a2 = argparse.Namespace(**vars(args))
+    a2.persons_per_gpu = max(64, 4 * (os.cpu_count() or 1))   # only the sample is evaluated
+    model = build_shard(a2, 0)
+    val, cores, desc, sec = cpu_sample(args, model, steps=max(1, args.steps), warmup=max(0, min(args.warmup, 1)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C4 sample: 6-latent coupled Van der Pol, irregular dt, 8 groups, T=100, eps=1e-6 central, rk4 h=min(dt)/30",
+                   "note": "reference R/Rcpp/odeint cannot be built here (no R, Armadillo, Boost); this is the oracle port of its "
+                           "algorithm, which omits the reference's per-call Rcpp::List lookups and is therefore faster than it"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import ctypes as C
+    import torch
+    import psydiff_b200 as pd
+    from psydiff_b200 import _lib, dist as pdist, flops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: psydiff_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = _lib.lib()
+
+    model = build_shard(args, rank)
+    if world > 1:
+        pdist.align_parameters(model)
+    pd.compileModel(model)
+    h = model["_handle"].ptr
+    pt = model["pars"]["parameterTable"]
+    N_local, T, P = pt.theta_index.shape[0], args.timepoints, len(pt.theta_labels)
+    N_total = N_local * world
+    n_inst = int(L.psy_n_instances(h))
+
+    peak = C.c_double(0.0)
+    _lib.check(L.psy_measure_fp64_peak(C.byref(peak)))
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return pdist.getGradientsSharded(model, return_total=True)
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    L.psy_counters_reset()
+    kernel_ms = []
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        g, total = step()
+        kernel_ms.append(L.psy_last_kernel_ms(h))
+    e1.record()
+    barrier()
+    launches = int(L.psy_launch_count())
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = float(ms.item()) / args.steps
+    value = N_total * T / (ms_per_step * 1e-3)
+
+    # end to end through the public API with HOST buffers: H2D of the dataset + theta, evaluation, D2H of the result
+    obs_host = model["data"]["observations"]
+    h2d = obs_host.nbytes + model["data"]["dt"].nbytes + 8 * P
+    d2h = 8 * (5 * P + 2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = 1
+    for _ in range(e2e_steps):
+        pd.uploadData(model)
+        step()
+    barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = N_total * T / float(e2e_s.item())
+
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (psy_filter_kernel): executed FP64 flops of this rank's launch / its event-timed duration
+    ks = np.asarray(kernel_ms)
+    dtv = model["data"]["dt"]
+    hstep = float(model["timeStep"][0])
+    # dt values in C4 are continuous; the step count is floor-like, so bin dt to 1e-3 resolution for the tally
+    qd = np.round(dtv, 3)
+    udt, cnt = np.unique(qd, return_counts=True)
+    steps_of = np.array([flops.rk4_step_count(float(d), hstep) if d != 0 else 0 for d in udt])
+    rk4_total_per_person_avg = float((steps_of * cnt).sum()) / N_local
+    inst_per_person = n_inst / N_local
+    fl_inst = flops.kernel_flops(6, 6, C4_FF, C4_FH, rk4_total_per_person_avg, T, l_diag=True)
+    fl_survey = flops.survey_flops(6, 6, C4_FF, C4_FH, rk4_total_per_person_avg, T)
+    k_ms = float(ks.mean())
+    achieved = fl_inst * n_inst / (k_ms * 1e-3) / 1e12
+    regs, loc, mt = C.c_int(), C.c_int(), C.c_int()
+    L.psy_kernel_info(h, C.byref(regs), C.byref(loc), C.byref(mt))
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {
+            "workload": f"C4: 6-latent coupled Van der Pol (n=m=6), irregular dt, 8 groups, P={P} ({inst_per_person:.0f} filter "
+                        f"instances/person), {N_local} persons/GPU x T={T} ({N_total} persons total), -2LL + full central FD gradient, "
+                        f"eps=1e-6, rk4 h=min(dt)/30 (avg {rk4_total_per_person_avg / max(T - 1, 1):.1f} steps/interval)",
+            "persons_per_gpu": N_local, "timepoints": T, "n_theta": P, "instances_per_gpu": n_inst,
+            "l2": "inputs (observations %.0f MB/GPU) larger than the 126 MB L2" % (obs_host.nbytes / 1e6),
+            "parallelism": f"persons sharded over {world} GPU(s), one all-reduce of {5 * P + 2} doubles per step",
+        },
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {
+            "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
+            "traffic": None, "kernel": "psy_filter_kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
+            "flops_per_instance": fl_inst, "flops_per_instance_survey_formula": fl_survey,
+            "achieved_survey_formula": fl_survey * n_inst / (k_ms * 1e-3) / 1e12,
+            "peak_source": "measured: dependent-free DFMA kernel (psy_measure_fp64_peak) on this GPU; MEASURED_PEAKS.json has no FP64 entry",
+            "registers": regs.value, "local_bytes": loc.value,
+            "hbm_algorithmic_bytes": int(obs_host.nbytes + dtv.nbytes + 8 * n_inst),
+        },
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        val, cores, desc, sec = cpu_sample(args, model)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "seconds": sec}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -103,6 +103,14 @@ int psy_grad_level(psy_model* mdl, const double* theta, double eps, int directio
 int psy_grad_resolve(psy_model* mdl, const double* partial_host, double eps, int level, int n_eps, int direction,
                      unsigned char* need_side, int* done);
 int psy_grad_finish(psy_model* mdl, int direction, double* grad, double* m2ll_total);
+/* The same bookkeeping without a device handle (psy_grad_resolve / psy_grad_finish delegate to it): usable on any
+ * host, e.g. by a coordinator process or in CPU tests of the multi-rank protocol. */
+typedef struct psy_sweep psy_sweep;
+psy_sweep* psy_sweep_create(int n_theta);
+void psy_sweep_destroy(psy_sweep* s);
+int psy_sweep_resolve(psy_sweep* s, const double* partial_host, double eps, int level, int n_eps, int direction,
+                      unsigned char* need_side, int* done);
+int psy_sweep_finish(psy_sweep* s, int direction, double* grad, double* m2ll_total);
 
 /* ---- instrumentation ------------------------------------------------------------------------------------ */
 /* device time (ms, CUDA events on the launch stream) of the last filter-kernel launch, its instance count and

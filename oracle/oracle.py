@@ -31,12 +31,17 @@ def _compile(src_path: str, out: str, extra=()):
     os.replace(tmp, out)
 
 
-def build(force=False, count_flops=False) -> str:
-    """Compile the oracle library (g++ -O2 -ffp-contract=off).  Returns the path of the shared object."""
+_EXT = ['-DPSY_REAL=long double', "-DPSY_EXT"]
+
+
+def build(force=False, count_flops=False, extended=False) -> str:
+    """Compile the oracle library (g++ -O2 -ffp-contract=off).  ``extended`` builds the same source with x87 80-bit
+    long double arithmetic (used to bound the double build's own rounding noise).  Returns the shared object path."""
     src = os.path.join(_HERE, "psy_oracle.cpp")
-    out = os.path.join(_BUILD, "libpsy_oracle_flops.so" if count_flops else "libpsy_oracle.so")
+    name = "libpsy_oracle" + ("_flops" if count_flops else "") + ("_ext" if extended else "") + ".so"
+    out = os.path.join(_BUILD, name)
     if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
-        _compile(src, out, ["-DPSY_COUNT_FLOPS"] if count_flops else [])
+        _compile(src, out, (["-DPSY_COUNT_FLOPS"] if count_flops else []) + (_EXT if extended else []))
     return out
 
 
@@ -56,10 +61,10 @@ class psy_oracle_problem(C.Structure):
 _libs = {}
 
 
-def _lib(count_flops=False):
-    key = bool(count_flops)
+def _lib(count_flops=False, extended=False):
+    key = (bool(count_flops), bool(extended))
     if key not in _libs:
-        L = C.CDLL(build(count_flops=count_flops))
+        L = C.CDLL(build(count_flops=count_flops, extended=extended))
         L.psy_oracle_fit.restype = C.c_int
         L.psy_oracle_fit.argtypes = [C.POINTER(psy_oracle_problem), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                      C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
@@ -99,7 +104,7 @@ def emit_host_cpp(spec) -> tuple:
                 seen.add(t)
                 c = spec.container(t)
                 if c.kind == "double":
-                    out.append(f"  const double {t} = plist[{off[t]}];\n")
+                    out.append(f"  const real {t} = plist[{off[t]}];\n")
                 else:
                     out.append(f"  ol::Mat {t}(plist + {off[t]}, {c.shape[0]}, {c.shape[1]});\n")
         return "".join(out)
@@ -108,12 +113,12 @@ def emit_host_cpp(spec) -> tuple:
     src = f"""// generated by oracle/oracle.py — user equations for the CPU oracle
 #include "{os.path.join(_HERE, 'psy_oracle_lang.hpp')}"
 using std::exp; using std::log; using std::pow; using std::sqrt; using std::sin; using std::cos; using std::tanh; using std::fabs;
-extern "C" void psy_user_drift(const double* x_, double* dx_, const double* plist, int person, double t) {{
+extern "C" void psy_user_drift(const real* x_, real* dx_, const real* plist, int person, real t) {{
   const ol::Vec x(x_, {n}); ol::Vec dx({n});
 {binds(spec.latentEquations)}  {spec.latentEquations.strip()}
   for (int i = 0; i < {n}; i++) dx_[i] = dx.v[i];
 }}
-extern "C" void psy_user_meas(const double* x_, double* y_, const double* plist, int person, double t) {{
+extern "C" void psy_user_meas(const real* x_, real* y_, const real* plist, int person, real t) {{
   const ol::Vec x(x_, {n}); ol::Vec y({m});
 {binds(spec.manifestEquations)}  {spec.manifestEquations.strip()}
   for (int i = 0; i < {m}; i++) y_[i] = y.v[i];
@@ -125,19 +130,19 @@ extern "C" void psy_user_meas(const double* x_, double* y_, const double* plist,
 class Oracle:
     """CPU oracle bound to one model object (built by psydiff_b200.newPsydiff)."""
 
-    def __init__(self, model, count_flops=False):
+    def __init__(self, model, count_flops=False, extended=False):
         spec = model["_spec"]
         self.model, self.spec = model, spec
-        self.L = _lib(count_flops)
+        self.L = _lib(count_flops, extended)
         src, off, plen = emit_host_cpp(spec)
-        h = hashlib.sha1(src.encode()).hexdigest()[:16]
+        h = hashlib.sha1(src.encode()).hexdigest()[:16] + ("_ext" if extended else "")
         so = os.path.join(_BUILD, f"user_{h}.so")
         if not os.path.exists(so):
             os.makedirs(_BUILD, exist_ok=True)
             cpp = os.path.join(_BUILD, f"user_{h}.cpp")
             with open(cpp, "w") as f:
                 f.write(src)
-            _compile(cpp, so)
+            _compile(cpp, so, _EXT if extended else [])
         self.user = C.CDLL(so)
         self.off, self.plen = off, plen
         base = np.zeros(plen)

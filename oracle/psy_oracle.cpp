@@ -33,6 +33,11 @@ static thread_local unsigned long long g_flops = 0;
 
 namespace {
 
+#ifndef PSY_REAL
+#define PSY_REAL double
+#endif
+typedef PSY_REAL real;  // long double in the extended-precision build used to bound the oracle's own rounding noise
+
 constexpr int NMAX = 12;            // max latent dimension
 constexpr int SMAX = 2 * NMAX + 1;  // max sigma points
 constexpr int MMAX = 16;            // max manifest dimension
@@ -41,13 +46,13 @@ constexpr int MMAX = 16;            // max manifest dimension
 
 // user equation signature emitted by oracle/codegen_host.py (mirrors R/prepareModel.R:479-505:
 // latentEquation(x, pars, person, t) -> dx ; measurementEquation(x, pars, person, t) -> y)
-typedef void (*user_fn)(const double* x, double* out, const double* plist, int person, double t);
+typedef void (*user_fn)(const real* x, real* out, const real* plist, int person, real t);
 
 struct Settings {
   int n, m;
-  double alpha, beta, kappa;
+  real alpha, beta, kappa;
   int stepper;       // 0 = rk4 (integrate_const), 1 = runge_kutta_dopri5 (integrate), 2 = "default"
-  double h;          // timeStep[0]  (Q2: later entries can never repair a NaN state, R/modelTemplate.R:324-346)
+  real h;          // timeStep[0]  (Q2: later entries can never repair a NaN state, R/modelTemplate.R:324-346)
   int sr;            // 1 = SR variant (R/modelTemplate.R:165-420), 0 = covariance variant (:583-847)
   int skip_update;   // fitModel(skipUpdate)
   // offsets of the special containers inside the flat parameter list
@@ -58,17 +63,17 @@ struct Settings {
 struct Ctx {
   const Settings* s;
   user_fn drift, meas;
-  const double* plist;
+  const real* plist;
   int person;
-  double c, sqrtc;
-  double wm[SMAX], wc[SMAX];
-  double L[NMAX * NMAX];   // logChol2Chol(LLogChol) (computeL, R/modelTemplate.R:77-83) — hoisted, constant per person
-  double LLt[NMAX * NMAX]; // L*Qc*L' with Qc = I (R/modelTemplate.R:104, 132)
+  real c, sqrtc;
+  real wm[SMAX], wc[SMAX];
+  real L[NMAX * NMAX];   // logChol2Chol(LLogChol) (computeL, R/modelTemplate.R:77-83) — hoisted, constant per person
+  real LLt[NMAX * NMAX]; // L*Qc*L' with Qc = I (R/modelTemplate.R:104, 132)
 };
 
 // inst/include/psydiffInternals.h:18-33  getMeanWeights_C / getCovWeights_C
-void ut_weights(int n, double alpha, double beta, double kappa, double* wm, double* wc) {
-  double lambda = alpha * alpha * (n + kappa) - n;
+void ut_weights(int n, real alpha, real beta, real kappa, real* wm, real* wc) {
+  real lambda = alpha * alpha * (n + kappa) - n;
   int s = 2 * n + 1;
   for (int i = 0; i < s; i++) { wm[i] = 1 / (2 * (n + lambda)); wc[i] = 1 / (2 * (n + lambda)); }
   wm[0] = lambda / (n + lambda);
@@ -76,17 +81,17 @@ void ut_weights(int n, double alpha, double beta, double kappa, double* wm, doub
 }
 
 // inst/include/psydiffInternals.h:35-44  getWMatrix_C : W = (I - wm 1')diag(wc)(I - wm 1')'
-void w_matrix(int s, const double* wm, const double* wc, double* W) {
-  std::vector<double> D(s * s);
+void w_matrix(int s, const real* wm, const real* wc, real* W) {
+  std::vector<real> D(s * s);
   for (int j = 0; j < s; j++) for (int i = 0; i < s; i++) D[IX(i, j, s)] = (i == j ? 1.0 : 0.0) - wm[i];
   for (int j = 0; j < s; j++) for (int i = 0; i < s; i++) {
-    double acc = 0; for (int k = 0; k < s; k++) acc += D[IX(i, k, s)] * wc[k] * D[IX(j, k, s)];
+    real acc = 0; for (int k = 0; k < s; k++) acc += D[IX(i, k, s)] * wc[k] * D[IX(j, k, s)];
     W[IX(i, j, s)] = acc;
   }
 }
 
 // inst/include/psydiffInternals.h:4-16  getSigmaPoints_C (covarianceIsRoot = true)
-void sigma_points(int n, const double* m, const double* A, double sqrtc, double* X) {
+void sigma_points(int n, const real* m, const real* A, real sqrtc, real* X) {
   for (int i = 0; i < n; i++) X[IX(i, 0, n)] = 0.0 + m[i];
   for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) {
     X[IX(i, 1 + j, n)] = sqrtc * A[IX(i, j, n)] + m[i];
@@ -96,21 +101,21 @@ void sigma_points(int n, const double* m, const double* A, double sqrtc, double*
 }
 
 // inst/include/psydiffInternals.h:46-60  computeMeanFromSigmaPoints_C + getAFromSigmaPoints_C (full n x n)
-void get_A(int n, const double* X, const double* wm, double sqrtc, double* A) {
-  int s = 2 * n + 1; double mean[NMAX];
-  for (int i = 0; i < n; i++) { double a = 0; for (int k = 0; k < s; k++) a += X[IX(i, k, n)] * wm[k]; mean[i] = a; }
+void get_A(int n, const real* X, const real* wm, real sqrtc, real* A) {
+  int s = 2 * n + 1; real mean[NMAX];
+  for (int i = 0; i < n; i++) { real a = 0; for (int k = 0; k < s; k++) a += X[IX(i, k, n)] * wm[k]; mean[i] = a; }
   for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) A[IX(i, j, n)] = (X[IX(i, 1 + j, n)] - mean[i]) / sqrtc;
   FL(2 * n * s + 2 * n * n);
 }
 
 // arma::inv(arma::trimatl(A)) (R/modelTemplate.R:97, psydiffInternals.h:125,201): forward substitution on the
 // lower triangle only (LAPACK dtrtri equivalent); strict upper of the result is exactly zero.
-void tri_inv_lower(int n, const double* A, int ld, double* Ai) {
+void tri_inv_lower(int n, const real* A, int ld, real* Ai) {
   for (int j = 0; j < n; j++) {
     for (int i = 0; i < n; i++) Ai[IX(i, j, n)] = 0.0;
     Ai[IX(j, j, n)] = 1.0 / A[IX(j, j, ld)];
     for (int i = j + 1; i < n; i++) {
-      double acc = 0; for (int k = j; k < i; k++) acc += A[IX(i, k, ld)] * Ai[IX(k, j, n)];
+      real acc = 0; for (int k = j; k < i; k++) acc += A[IX(i, k, ld)] * Ai[IX(k, j, n)];
       Ai[IX(i, j, n)] = -acc / A[IX(i, i, ld)];
     }
   }
@@ -119,20 +124,20 @@ void tri_inv_lower(int n, const double* A, int ld, double* Ai) {
 
 // odeintModel::operator() (R/modelTemplate.R:138-163) with getMMatrix (:85-135) and getPhi_C (Internals.h:69-75).
 // The drift is evaluated ONCE per column (the reference evaluates it twice with identical results, :106-109, :155-157).
-void rhs(const Ctx& cx, const double* X, double* dX, double t) {
+void rhs(const Ctx& cx, const real* X, real* dX, real t) {
   const int n = cx.s->n, s = 2 * n + 1;
-  double A[NMAX * NMAX], Ai[NMAX * NMAX], F[NMAX * SMAX];
+  real A[NMAX * NMAX], Ai[NMAX * NMAX], F[NMAX * SMAX];
   get_A(n, X, cx.wm, cx.sqrtc, A);                      // :94 / :143 (same value both times)
   tri_inv_lower(n, A, n, Ai);                           // :97
   for (int co = 0; co < s; co++) cx.drift(X + co * n, F + co * n, cx.plist, cx.person, t);  // :106-109
-  double mx[NMAX], mf[NMAX];
+  real mx[NMAX], mf[NMAX];
   for (int i = 0; i < n; i++) { mx[i] = 0; mf[i] = 0; }
   for (int co = 0; co < s; co++) for (int i = 0; i < n; i++) {   // :113-116
     mx[i] += cx.wm[co] * X[IX(i, co, n)]; mf[i] += cx.wm[co] * F[IX(i, co, n)];
   }
-  double S1[NMAX * NMAX];  // sum1 + sum2 + L L'   (:119-133)
+  real S1[NMAX * NMAX];  // sum1 + sum2 + L L'   (:119-133)
   for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) {
-    double s1 = 0, s2 = 0;
+    real s1 = 0, s2 = 0;
     for (int co = 0; co < s; co++) {
       s1 += cx.wc[co] * (X[IX(i, co, n)] - mx[i]) * (F[IX(j, co, n)] - mf[j]);
       s2 += cx.wc[co] * (F[IX(i, co, n)] - mf[i]) * (X[IX(j, co, n)] - mx[j]);
@@ -140,18 +145,18 @@ void rhs(const Ctx& cx, const double* X, double* dX, double t) {
     S1[IX(i, j, n)] = s1 + s2 + cx.LLt[IX(i, j, n)];
   }
   // M = invCov * S1 * invCov'
-  double T1[NMAX * NMAX], M[NMAX * NMAX];
+  real T1[NMAX * NMAX], M[NMAX * NMAX];
   for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) {
-    double a = 0; for (int k = 0; k < n; k++) a += Ai[IX(i, k, n)] * S1[IX(k, j, n)]; T1[IX(i, j, n)] = a;
+    real a = 0; for (int k = 0; k < n; k++) a += Ai[IX(i, k, n)] * S1[IX(k, j, n)]; T1[IX(i, j, n)] = a;
   }
   for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) {
-    double a = 0; for (int k = 0; k < n; k++) a += T1[IX(i, k, n)] * Ai[IX(j, k, n)]; M[IX(i, j, n)] = a;
+    real a = 0; for (int k = 0; k < n; k++) a += T1[IX(i, k, n)] * Ai[IX(j, k, n)]; M[IX(i, j, n)] = a;
   }
   // Phi(M): trimatl with halved diagonal (Internals.h:69-75); APhi = A * Phi (full A as returned by getA, :150)
-  double APhi[NMAX * NMAX];
+  real APhi[NMAX * NMAX];
   for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) {
-    double a = 0;
-    for (int k = j; k < n; k++) { double ph = (k == j) ? 0.5 * M[IX(k, j, n)] : M[IX(k, j, n)]; a += A[IX(i, k, n)] * ph; }
+    real a = 0;
+    for (int k = j; k < n; k++) { real ph = (k == j) ? 0.5 * M[IX(k, j, n)] : M[IX(k, j, n)]; a += A[IX(i, k, n)] * ph; }
     APhi[IX(i, j, n)] = a;
   }
   // dxdt.col(co) = sigmaPredict * meanWeights + sqrt(c) * augmented.col(co)  (:159-161)
@@ -166,17 +171,17 @@ void rhs(const Ctx& cx, const double* X, double* dX, double t) {
 
 // Boost.odeint integrate_const(runge_kutta4, sys, x, t0, t1, h) — call sites R/modelTemplate.R:327-329, 335-337.
 // Rule T1: steps while (time + h) - t1 <= DBL_EPSILON, time = t0 + step*h, remainder dropped.
-int rk4_steps(double t0, double t1, double h) {
-  int step = 0; double time = t0;
+int rk4_steps(real t0, real t1, real h) {
+  int step = 0; real time = t0;
   if (!(h > 0)) return 0;
-  while ((time + h) - t1 <= DBL_EPSILON) { ++step; time = t0 + (double)step * h; if (step > 100000000) break; }
+  while ((time + h) - t1 <= DBL_EPSILON) { ++step; time = t0 + (real)step * h; if (step > 100000000) break; }
   return step;
 }
 
-int integrate_const_rk4(const Ctx& cx, double* X, double t0, double t1, double h) {
+int integrate_const_rk4(const Ctx& cx, real* X, real t0, real t1, real h) {
   const int n = cx.s->n, len = n * (2 * n + 1);
-  double k1[NMAX * SMAX], k2[NMAX * SMAX], k3[NMAX * SMAX], k4[NMAX * SMAX], xt[NMAX * SMAX];
-  int step = 0; double time = t0;
+  real k1[NMAX * SMAX], k2[NMAX * SMAX], k3[NMAX * SMAX], k4[NMAX * SMAX], xt[NMAX * SMAX];
+  int step = 0; real time = t0;
   while ((time + h) - t1 <= DBL_EPSILON) {
     // runge_kutta4::do_step (generic RK form: explicit zero coefficients are multiplied in too)
     rhs(cx, X, k1, time);
@@ -189,7 +194,7 @@ int integrate_const_rk4(const Ctx& cx, double* X, double t0, double t1, double h
     for (int i = 0; i < len; i++)
       X[i] = 1.0 * X[i] + (h * (1.0 / 6.0)) * k1[i] + (h * (1.0 / 3.0)) * k2[i] + (h * (1.0 / 3.0)) * k3[i] + (h * (1.0 / 6.0)) * k4[i];
     FL(14 * len);
-    ++step; time = t0 + (double)step * h;
+    ++step; time = t0 + (real)step * h;
   }
   return step;
 }
@@ -197,18 +202,18 @@ int integrate_const_rk4(const Ctx& cx, double* X, double t0, double t1, double h
 // Boost.odeint integrate(sys, x, t0, t1, dt) = integrate_adaptive(controlled_runge_kutta<runge_kutta_dopri5>(1e-6,1e-6))
 // — call sites R/modelTemplate.R:331-333, 340-342.  Rule T2.  Returns -1 on step-size underflow
 // (odeint throws after too many failed tries) after poisoning X with NaN.
-int integrate_dopri5(const Ctx& cx, double* X, double t0, double t1, double dt) {
+int integrate_dopri5(const Ctx& cx, real* X, real t0, real t1, real dt) {
   const int n = cx.s->n, len = n * (2 * n + 1);
-  const double eps_abs = 1e-6, eps_rel = 1e-6;
-  static const double a21 = 1.0 / 5, a31 = 3.0 / 40, a32 = 9.0 / 40, a41 = 44.0 / 45, a42 = -56.0 / 15, a43 = 32.0 / 9,
+  const real eps_abs = 1e-6, eps_rel = 1e-6;
+  static const real a21 = 1.0 / 5, a31 = 3.0 / 40, a32 = 9.0 / 40, a41 = 44.0 / 45, a42 = -56.0 / 15, a43 = 32.0 / 9,
       a51 = 19372.0 / 6561, a52 = -25360.0 / 2187, a53 = 64448.0 / 6561, a54 = -212.0 / 729,
       a61 = 9017.0 / 3168, a62 = -355.0 / 33, a63 = 46732.0 / 5247, a64 = 49.0 / 176, a65 = -5103.0 / 18656,
       c1 = 35.0 / 384, c3 = 500.0 / 1113, c4 = 125.0 / 192, c5 = -2187.0 / 6784, c6 = 11.0 / 84;
-  static const double dc1 = c1 - 5179.0 / 57600, dc3 = c3 - 7571.0 / 16695, dc4 = c4 - 393.0 / 640,
+  static const real dc1 = c1 - 5179.0 / 57600, dc3 = c3 - 7571.0 / 16695, dc4 = c4 - 393.0 / 640,
       dc5 = c5 - (-92097.0 / 339200), dc6 = c6 - 187.0 / 2100, dc7 = -1.0 / 40;
-  double k1[NMAX * SMAX], k2[NMAX * SMAX], k3[NMAX * SMAX], k4[NMAX * SMAX], k5[NMAX * SMAX], k6[NMAX * SMAX], k7[NMAX * SMAX];
-  double xt[NMAX * SMAX], xn[NMAX * SMAX];
-  double t = t0; int count = 0;
+  real k1[NMAX * SMAX], k2[NMAX * SMAX], k3[NMAX * SMAX], k4[NMAX * SMAX], k5[NMAX * SMAX], k6[NMAX * SMAX], k7[NMAX * SMAX];
+  real xt[NMAX * SMAX], xn[NMAX * SMAX];
+  real t = t0; int count = 0;
   rhs(cx, X, k1, t);  // fresh controlled stepper per call: FSAL derivative initialised here
   while (t1 - t > DBL_EPSILON) {
     if ((t + dt) - t1 > DBL_EPSILON) dt = t1 - t;
@@ -227,24 +232,24 @@ int integrate_dopri5(const Ctx& cx, double* X, double t0, double t1, double dt) 
       rhs(cx, xt, k6, t + dt);
       for (int i = 0; i < len; i++) xn[i] = X[i] + dt * c1 * k1[i] + dt * c3 * k3[i] + dt * c4 * k4[i] + dt * c5 * k5[i] + dt * c6 * k6[i];
       rhs(cx, xn, k7, t + dt);
-      double err = 0;
+      real err = 0;
       bool bad = false;
       for (int i = 0; i < len; i++) {
-        double xe = dt * dc1 * k1[i] + dt * dc3 * k3[i] + dt * dc4 * k4[i] + dt * dc5 * k5[i] + dt * dc6 * k6[i] + dt * dc7 * k7[i];
-        double e = std::fabs(xe) / (eps_abs + eps_rel * (std::fabs(X[i]) + std::fabs(dt) * std::fabs(k1[i])));
+        real xe = dt * dc1 * k1[i] + dt * dc3 * k3[i] + dt * dc4 * k4[i] + dt * dc5 * k5[i] + dt * dc6 * k6[i] + dt * dc7 * k7[i];
+        real e = std::fabs(xe) / (eps_abs + eps_rel * (std::fabs(X[i]) + std::fabs(dt) * std::fabs(k1[i])));
         if (e != e) bad = true;
         if (e > err) err = e;
       }
       FL(45 * len);
       if (bad) { for (int i = 0; i < len; i++) X[i] = NAN; return -1; }  // NaN error: odeint would accept garbage; state is NaN either way
       if (err > 1.0) {
-        dt *= std::max(0.9 * std::pow(err, -1.0 / 3.0), 0.2);
+        dt *= std::max<real>(0.9 * std::pow(err, (real)(-1.0 / 3.0)), 0.2);
         continue;
       }
       t += dt;
-      if (err < 0.5) { double e5 = std::max(std::pow(5.0, -5.0), err); dt *= 0.9 * std::pow(e5, -1.0 / 5.0); }
-      std::memcpy(X, xn, sizeof(double) * len);
-      std::memcpy(k1, k7, sizeof(double) * len);
+      if (err < 0.5) { real e5 = std::max<real>(std::pow(5.0, -5.0), err); dt *= 0.9 * std::pow(e5, (real)(-1.0 / 5.0)); }
+      std::memcpy(X, xn, sizeof(real) * len);
+      std::memcpy(k1, k7, sizeof(real) * len);
       break;
     }
     ++count;
@@ -255,22 +260,22 @@ int integrate_dopri5(const Ctx& cx, double* X, double t0, double t1, double dt) 
 // qr_C (Internals.h:167-171): R factor of arma::qr_econ(X), X rows x cols (rows >= cols), via Householder
 // reflections (LAPACK dgeqrf convention).  Signs of R's rows are implementation-defined and are normalised by the
 // caller's cholupdate.  R is cols x cols upper triangular, column-major.
-void qr_R(int rows, int cols, const double* Xin, double* R) {
-  std::vector<double> Xv(Xin, Xin + (size_t)rows * cols);
-  double* X = Xv.data();
+void qr_R(int rows, int cols, const real* Xin, real* R) {
+  std::vector<real> Xv(Xin, Xin + (size_t)rows * cols);
+  real* X = Xv.data();
   for (int k = 0; k < cols; k++) {
-    double norm = 0; for (int i = k; i < rows; i++) norm += X[IX(i, k, rows)] * X[IX(i, k, rows)];
+    real norm = 0; for (int i = k; i < rows; i++) norm += X[IX(i, k, rows)] * X[IX(i, k, rows)];
     norm = std::sqrt(norm);
     if (norm == 0.0) continue;
-    double alpha = X[IX(k, k, rows)] > 0 ? -norm : norm;
-    std::vector<double> v(rows, 0.0);
+    real alpha = X[IX(k, k, rows)] > 0 ? -norm : norm;
+    std::vector<real> v(rows, 0.0);
     for (int i = k; i < rows; i++) v[i] = X[IX(i, k, rows)];
     v[k] -= alpha;
-    double vtv = 0; for (int i = k; i < rows; i++) vtv += v[i] * v[i];
+    real vtv = 0; for (int i = k; i < rows; i++) vtv += v[i] * v[i];
     if (vtv == 0.0) continue;
     for (int j = k; j < cols; j++) {
-      double dot = 0; for (int i = k; i < rows; i++) dot += v[i] * X[IX(i, j, rows)];
-      double f = 2.0 * dot / vtv;
+      real dot = 0; for (int i = k; i < rows; i++) dot += v[i] * X[IX(i, j, rows)];
+      real f = 2.0 * dot / vtv;
       for (int i = k; i < rows; i++) X[IX(i, j, rows)] -= f * v[i];
     }
   }
@@ -280,15 +285,15 @@ void qr_R(int rows, int cols, const double* Xin, double* R) {
 
 // cholupdate_C (Internals.h:133-165), literal — including the v^0.25 scaling (quirk Q3) and |v| for v<0.
 // dir: +1 update, -1 downdate.  L is n x n column-major (full storage), x length n.
-void cholupdate(int n, double* L, const double* xin, double v, int dir) {
-  double x[MMAX > NMAX ? MMAX : NMAX];
+void cholupdate(int n, real* L, const real* xin, real v, int dir) {
+  real x[MMAX > NMAX ? MMAX : NMAX];
   if (v < 0) v = -1 * v;
   v = std::pow(v, .25);
   for (int i = 0; i < n; i++) x[i] = v * xin[i];
   for (int k = 0; k < n; k++) {
-    double r = std::sqrt(std::pow(L[IX(k, k, n)], 2.0) + dir * std::pow(x[k], 2.0));
-    double c = r / L[IX(k, k, n)];
-    double s = x[k] / L[IX(k, k, n)];
+    real r = std::sqrt(std::pow(L[IX(k, k, n)], 2.0) + dir * std::pow(x[k], 2.0));
+    real c = r / L[IX(k, k, n)];
+    real s = x[k] / L[IX(k, k, n)];
     L[IX(k, k, n)] = r;
     if (k < n - 1) {
       for (int i = k + 1; i < n; i++) L[IX(i, k, n)] = (L[IX(i, k, n)] + dir * s * x[i]) / c;
@@ -299,42 +304,42 @@ void cholupdate(int n, double* L, const double* xin, double v, int dir) {
 }
 
 // predictSquareRootOfS_C (Internals.h:174-198).  Y o x s (rows = non-missing manifests), mu o, Rchol o x o.
-void predict_srS(int o, int s, const double* Y, const double* mu, const double* Rchol, double wc0, double wc1, double* srS) {
+void predict_srS(int o, int s, const real* Y, const real* mu, const real* Rchol, real wc0, real wc1, real* srS) {
   int cols = s + o;
-  std::vector<double> Tt((size_t)cols * o);  // trans(tempMat): (s+o) x o
-  double sq = std::sqrt(wc1);
+  std::vector<real> Tt((size_t)cols * o);  // trans(tempMat): (s+o) x o
+  real sq = std::sqrt(wc1);
   for (int co = 0; co < s; co++) for (int i = 0; i < o; i++) Tt[IX(co, i, cols)] = sq * (Y[IX(i, co, o)] - mu[i]);
   for (int j = 0; j < o; j++) for (int i = 0; i < o; i++) Tt[IX(s + j, i, cols)] = Rchol[IX(i, j, o)];
-  double R[MMAX * MMAX];
+  real R[MMAX * MMAX];
   qr_R(cols, o, Tt.data(), R);
   for (int j = 0; j < o; j++) for (int i = 0; i < o; i++) srS[IX(i, j, o)] = R[IX(j, i, o)];  // trans(R)
-  double d0[MMAX]; for (int i = 0; i < o; i++) d0[i] = Y[IX(i, 0, o)] - mu[i];
+  real d0[MMAX]; for (int i = 0; i < o; i++) d0[i] = Y[IX(i, 0, o)] - mu[i];
   if (wc0 < 0) cholupdate(o, srS, d0, -1 * wc0, -1); else cholupdate(o, srS, d0, wc0, +1);
   for (int j = 0; j < o; j++) for (int i = 0; i < j; i++) srS[IX(i, j, o)] = 0.0;  // trimatl
 }
 
 // general inverse / determinant by LU with partial pivoting (arma::inv / arma::det → LAPACK dgetrf/dgetri),
 // used by the covariance variant (Internals.h:90-92, 103-115).  Returns det; Ainv may be null.
-double lu_inv_det(int n, const double* Ain, double* Ainv) {
-  double A[MMAX * MMAX], B[MMAX * MMAX]; int piv[MMAX];
+real lu_inv_det(int n, const real* Ain, real* Ainv) {
+  real A[MMAX * MMAX], B[MMAX * MMAX]; int piv[MMAX];
   for (int i = 0; i < n * n; i++) A[i] = Ain[i];
   for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) B[IX(i, j, n)] = (i == j);
-  double det = 1;
+  real det = 1;
   for (int k = 0; k < n; k++) {
-    int p = k; double best = std::fabs(A[IX(k, k, n)]);
+    int p = k; real best = std::fabs(A[IX(k, k, n)]);
     for (int i = k + 1; i < n; i++) if (std::fabs(A[IX(i, k, n)]) > best) { best = std::fabs(A[IX(i, k, n)]); p = i; }
     piv[k] = p;
     if (p != k) { det = -det; for (int j = 0; j < n; j++) { std::swap(A[IX(k, j, n)], A[IX(p, j, n)]); std::swap(B[IX(k, j, n)], B[IX(p, j, n)]); } }
-    double d = A[IX(k, k, n)]; det *= d;
+    real d = A[IX(k, k, n)]; det *= d;
     for (int i = k + 1; i < n; i++) {
-      double f = A[IX(i, k, n)] / d; A[IX(i, k, n)] = f;
+      real f = A[IX(i, k, n)] / d; A[IX(i, k, n)] = f;
       for (int j = k + 1; j < n; j++) A[IX(i, j, n)] -= f * A[IX(k, j, n)];
       for (int j = 0; j < n; j++) B[IX(i, j, n)] -= f * B[IX(k, j, n)];
     }
   }
   if (Ainv) {
     for (int j = 0; j < n; j++) for (int i = n - 1; i >= 0; i--) {
-      double a = B[IX(i, j, n)]; for (int k = i + 1; k < n; k++) a -= A[IX(i, k, n)] * Ainv[IX(k, j, n)];
+      real a = B[IX(i, j, n)]; for (int k = i + 1; k < n; k++) a -= A[IX(i, k, n)] * Ainv[IX(k, j, n)];
       Ainv[IX(i, j, n)] = a / A[IX(i, i, n)];
     }
   }
@@ -343,14 +348,14 @@ double lu_inv_det(int n, const double* Ain, double* Ainv) {
 }
 
 // arma::chol(P, "lower") (R/modelTemplate.R:720).  Returns false if not positive definite (Armadillo throws).
-bool chol_lower(int n, const double* P, double* A) {
+bool chol_lower(int n, const real* P, real* A) {
   for (int i = 0; i < n * n; i++) A[i] = 0;
   for (int j = 0; j < n; j++) {
-    double d = P[IX(j, j, n)]; for (int k = 0; k < j; k++) d -= A[IX(j, k, n)] * A[IX(j, k, n)];
+    real d = P[IX(j, j, n)]; for (int k = 0; k < j; k++) d -= A[IX(j, k, n)] * A[IX(j, k, n)];
     if (!(d > 0)) return false;
     d = std::sqrt(d); A[IX(j, j, n)] = d;
     for (int i = j + 1; i < n; i++) {
-      double a = P[IX(i, j, n)]; for (int k = 0; k < j; k++) a -= A[IX(i, k, n)] * A[IX(j, k, n)];
+      real a = P[IX(i, j, n)]; for (int k = 0; k < j; k++) a -= A[IX(i, k, n)] * A[IX(j, k, n)];
       A[IX(i, j, n)] = a / d;
     }
   }
@@ -359,48 +364,48 @@ bool chol_lower(int n, const double* P, double* A) {
 }
 
 // logChol2Chol_C (Internals.h:205-209): exp() on the diagonal, everything else kept (full matrix)
-void logchol2chol(int n, const double* lc, double* out) {
+void logchol2chol(int n, const real* lc, real* out) {
   for (int i = 0; i < n * n; i++) out[i] = lc[i];
   for (int i = 0; i < n; i++) out[IX(i, i, n)] = std::exp(lc[IX(i, i, n)]);
 }
 
 // One person: the body of the person loop of fitModel (R/modelTemplate.R:244-411 SR, :660-838 covariance).
 // obs: T x m ROW-major slice for this person (obs[t*m + j]); dt: T.  latent (T x n) / pred (T x m) row-major, may be null.
-double fit_person(const Settings& st, user_fn drift, user_fn meas, const double* plist, int person,
+real fit_person(const Settings& st, user_fn drift, user_fn meas, const real* plist, int person,
                   int T, const double* obs, const double* dts, double* latent, double* pred) {
   const int n = st.n, m = st.m, s = 2 * n + 1;
   Ctx cx; cx.s = &st; cx.drift = drift; cx.meas = meas; cx.plist = plist; cx.person = person;
-  double kappa = st.kappa;
+  real kappa = st.kappa;
   if (n + kappa == 0) kappa -= 1;                                  // :192-196
   cx.c = std::pow(st.alpha, 2) * (n + kappa); cx.sqrtc = std::sqrt(cx.c);   // :197
   ut_weights(n, st.alpha, st.beta, kappa, cx.wm, cx.wc);            // :306-309
-  std::vector<double> W((size_t)s * s); w_matrix(s, cx.wm, cx.wc, W.data());  // :310
+  std::vector<real> W((size_t)s * s); w_matrix(s, cx.wm, cx.wc, W.data());  // :310
   logchol2chol(n, plist + st.off_L, cx.L);
   for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) {
-    double a = 0; for (int k = 0; k < n; k++) a += cx.L[IX(i, k, n)] * cx.L[IX(j, k, n)]; cx.LLt[IX(i, j, n)] = a;
+    real a = 0; for (int k = 0; k < n; k++) a += cx.L[IX(i, k, n)] * cx.L[IX(j, k, n)]; cx.LLt[IX(i, j, n)] = a;
   }
-  double mvec[NMAX], m_[NMAX], A[NMAX * NMAX], P[NMAX * NMAX], P_[NMAX * NMAX], Rchol[MMAX * MMAX], Rfull[MMAX * MMAX];
+  real mvec[NMAX], m_[NMAX], A[NMAX * NMAX], P[NMAX * NMAX], P_[NMAX * NMAX], Rchol[MMAX * MMAX], Rfull[MMAX * MMAX];
   for (int i = 0; i < n; i++) mvec[i] = plist[st.off_m0 + i];      // :275
   logchol2chol(n, plist + st.off_A0, A);                            // :276
   logchol2chol(m, plist + st.off_R, Rchol);                         // :277-278
   if (!st.sr) {                                                     // :694-698
-    for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) { double a = 0; for (int k = 0; k < n; k++) a += A[IX(i, k, n)] * A[IX(j, k, n)]; P[IX(i, j, n)] = a; }
-    for (int j = 0; j < m; j++) for (int i = 0; i < m; i++) { double a = 0; for (int k = 0; k < m; k++) a += Rchol[IX(i, k, m)] * Rchol[IX(j, k, m)]; Rfull[IX(i, j, m)] = a; }
+    for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) { real a = 0; for (int k = 0; k < n; k++) a += A[IX(i, k, n)] * A[IX(j, k, n)]; P[IX(i, j, n)] = a; }
+    for (int j = 0; j < m; j++) for (int i = 0; i < m; i++) { real a = 0; for (int k = 0; k < m; k++) a += Rchol[IX(i, k, m)] * Rchol[IX(j, k, m)]; Rfull[IX(i, j, m)] = a; }
   }
-  double m2ll = 0.0, timeSum = 0.0;
-  double X[NMAX * SMAX], Y[MMAX * SMAX], mu[MMAX];
+  real m2ll = 0.0, timeSum = 0.0;
+  real X[NMAX * SMAX], Y[MMAX * SMAX], mu[MMAX];
   for (int tp = 0; tp < T; tp++) {
-    timeSum += dts[tp];                                             // :285
-    const double* ob = obs + (size_t)tp * m;
+    timeSum += (real)dts[tp];                                             // :285
+    real ob[MMAX]; for (int j = 0; j < m; j++) ob[j] = obs[(size_t)tp * m + j];
     int nm[MMAX], o = 0;
     for (int j = 0; j < m; j++) if (std::isfinite(ob[j])) nm[o++] = j;   // :291-293
     for (int i = 0; i < n; i++) m_[i] = mvec[i];                    // :298
     if (!st.sr) {                                                   // :718-720
-      std::memcpy(P_, P, sizeof(double) * n * n);
+      std::memcpy(P_, P, sizeof(real) * n * n);
       if (!chol_lower(n, P_, A)) { m2ll = NAN; break; }             // Armadillo throws → caller sees failure
     }
     sigma_points(n, m_, A, cx.sqrtc, X);                            // :303
-    double endTime = dts[tp];
+    real endTime = (real)dts[tp];
     if (std::fabs(0.0 - endTime) > 0) {                             // :320 with fabs semantics (quirk Q1)
       if (st.stepper == 1) integrate_dopri5(cx, X, 0.0, endTime, st.h);
       else {
@@ -411,73 +416,73 @@ double fit_person(const Settings& st, user_fn drift, user_fn meas, const double*
         }
       }
       for (int i = 0; i < n; i++) m_[i] = X[IX(i, 0, n)];           // :348
-      double Af[NMAX * NMAX]; get_A(n, X, cx.wm, cx.sqrtc, Af);
+      real Af[NMAX * NMAX]; get_A(n, X, cx.wm, cx.sqrtc, Af);
       if (st.sr) {                                                  // :349  A = trimatl(getA(x))
         for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) A[IX(i, j, n)] = (i >= j) ? Af[IX(i, j, n)] : 0.0;
       } else {                                                      // :771  P_ = A A'
-        for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) { double a = 0; for (int k = 0; k < n; k++) a += Af[IX(i, k, n)] * Af[IX(j, k, n)]; P_[IX(i, j, n)] = a; }
+        for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) { real a = 0; for (int k = 0; k < n; k++) a += Af[IX(i, k, n)] * Af[IX(j, k, n)]; P_[IX(i, j, n)] = a; }
       }
     }
     for (int co = 0; co < s; co++) meas(X + co * n, Y + co * m, plist, person, timeSum);   // getY_, :353-355, :62-73
-    for (int j = 0; j < m; j++) { double a = 0; for (int co = 0; co < s; co++) a += Y[IX(j, co, m)] * cx.wm[co]; mu[j] = a; }  // :358
+    for (int j = 0; j < m; j++) { real a = 0; for (int co = 0; co < s; co++) a += Y[IX(j, co, m)] * cx.wm[co]; mu[j] = a; }  // :358
     FL(2 * m * s);
-    if (pred) for (int j = 0; j < m; j++) pred[(size_t)tp * m + j] = mu[j];   // :361
+    if (pred) for (int j = 0; j < m; j++) pred[(size_t)tp * m + j] = (double)mu[j];   // :361
     if (o > 0 && !st.skip_update) {
-      double Yo[MMAX * SMAX], muo[MMAX], Ro[MMAX * MMAX], res[MMAX];
+      real Yo[MMAX * SMAX], muo[MMAX], Ro[MMAX * MMAX], res[MMAX];
       for (int co = 0; co < s; co++) for (int a = 0; a < o; a++) Yo[IX(a, co, o)] = Y[IX(nm[a], co, m)];
       for (int a = 0; a < o; a++) { muo[a] = mu[nm[a]]; res[a] = ob[nm[a]] - mu[nm[a]]; }   // :374
       // C = X * W * Yo'  (predictC_C, Internals.h:85-88), literal dense W
-      double XW[NMAX * SMAX], C[NMAX * MMAX], K[NMAX * MMAX];
-      for (int co = 0; co < s; co++) for (int i = 0; i < n; i++) { double a = 0; for (int k = 0; k < s; k++) a += X[IX(i, k, n)] * W[IX(k, co, s)]; XW[IX(i, co, n)] = a; }
-      for (int b = 0; b < o; b++) for (int i = 0; i < n; i++) { double a = 0; for (int k = 0; k < s; k++) a += XW[IX(i, k, n)] * Yo[IX(b, k, o)]; C[IX(i, b, n)] = a; }
+      real XW[NMAX * SMAX], C[NMAX * MMAX], K[NMAX * MMAX];
+      for (int co = 0; co < s; co++) for (int i = 0; i < n; i++) { real a = 0; for (int k = 0; k < s; k++) a += X[IX(i, k, n)] * W[IX(k, co, s)]; XW[IX(i, co, n)] = a; }
+      for (int b = 0; b < o; b++) for (int i = 0; i < n; i++) { real a = 0; for (int k = 0; k < s; k++) a += XW[IX(i, k, n)] * Yo[IX(b, k, o)]; C[IX(i, b, n)] = a; }
       FL(2 * n * o * s + 2 * n * s);
       if (st.sr) {
         for (int b = 0; b < o; b++) for (int a = 0; a < o; a++) Ro[IX(a, b, o)] = Rchol[IX(nm[a], nm[b], m)];
-        double srS[MMAX * MMAX], Si[MMAX * MMAX];
+        real srS[MMAX * MMAX], Si[MMAX * MMAX];
         predict_srS(o, s, Yo, muo, Ro, cx.wc[0], cx.wc[1], srS);                      // :365
         tri_inv_lower(o, srS, o, Si);                                                 // computeK_SR_C, Internals.h:200-203
-        double CSt[NMAX * MMAX];
-        for (int b = 0; b < o; b++) for (int i = 0; i < n; i++) { double a = 0; for (int k = 0; k < o; k++) a += C[IX(i, k, n)] * Si[IX(b, k, o)]; CSt[IX(i, b, n)] = a; }
-        for (int b = 0; b < o; b++) for (int i = 0; i < n; i++) { double a = 0; for (int k = 0; k < o; k++) a += CSt[IX(i, k, n)] * Si[IX(k, b, o)]; K[IX(i, b, n)] = a; }
-        for (int i = 0; i < n; i++) { double a = 0; for (int b = 0; b < o; b++) a += K[IX(i, b, n)] * res[b]; mvec[i] = m_[i] + a; }   // :378
-        double U[NMAX * MMAX];                                                        // :382-386
-        for (int b = 0; b < o; b++) for (int i = 0; i < n; i++) { double a = 0; for (int k = 0; k < o; k++) a += K[IX(i, k, n)] * srS[IX(k, b, o)]; U[IX(i, b, n)] = a; }
+        real CSt[NMAX * MMAX];
+        for (int b = 0; b < o; b++) for (int i = 0; i < n; i++) { real a = 0; for (int k = 0; k < o; k++) a += C[IX(i, k, n)] * Si[IX(b, k, o)]; CSt[IX(i, b, n)] = a; }
+        for (int b = 0; b < o; b++) for (int i = 0; i < n; i++) { real a = 0; for (int k = 0; k < o; k++) a += CSt[IX(i, k, n)] * Si[IX(k, b, o)]; K[IX(i, b, n)] = a; }
+        for (int i = 0; i < n; i++) { real a = 0; for (int b = 0; b < o; b++) a += K[IX(i, b, n)] * res[b]; mvec[i] = m_[i] + a; }   // :378
+        real U[NMAX * MMAX];                                                        // :382-386
+        for (int b = 0; b < o; b++) for (int i = 0; i < n; i++) { real a = 0; for (int k = 0; k < o; k++) a += K[IX(i, k, n)] * srS[IX(k, b, o)]; U[IX(i, b, n)] = a; }
         for (int b = 0; b < o; b++) {
           cholupdate(n, A, U + b * n, 1.0, -1);
           for (int j = 0; j < n; j++) for (int i = 0; i < j; i++) A[IX(i, j, n)] = 0.0;
         }
         // computeIndividualM2LLChol_C (Internals.h:117-131)
-        double ld = 0; for (int a = 0; a < o; a++) ld += std::log(srS[IX(a, a, o)]);
-        double z[MMAX], dist = 0;
-        for (int a = 0; a < o; a++) { double acc = 0; for (int k = 0; k < o; k++) acc += Si[IX(a, k, o)] * res[k]; z[a] = acc; }
+        real ld = 0; for (int a = 0; a < o; a++) ld += std::log(srS[IX(a, a, o)]);
+        real z[MMAX], dist = 0;
+        for (int a = 0; a < o; a++) { real acc = 0; for (int k = 0; k < o; k++) acc += Si[IX(a, k, o)] * res[k]; z[a] = acc; }
         for (int a = 0; a < o; a++) dist += z[a] * z[a];
         m2ll += o * std::log(2 * M_PI) + 2 * ld + dist;                               // :390-392
         FL(4 * n * o * o + 2 * n * o + 2 * o * o + 4 * o);
       } else {
-        double S[MMAX * MMAX], Sinv[MMAX * MMAX];
+        real S[MMAX * MMAX], Sinv[MMAX * MMAX];
         // predictS_C (Internals.h:81-83): Yo W Yo' + R, then symmetrised (:790)
-        double YW[MMAX * SMAX];
-        for (int co = 0; co < s; co++) for (int a = 0; a < o; a++) { double acc = 0; for (int k = 0; k < s; k++) acc += Yo[IX(a, k, o)] * W[IX(k, co, s)]; YW[IX(a, co, o)] = acc; }
-        for (int b = 0; b < o; b++) for (int a = 0; a < o; a++) { double acc = 0; for (int k = 0; k < s; k++) acc += YW[IX(a, k, o)] * Yo[IX(b, k, o)]; S[IX(a, b, o)] = acc + Rfull[IX(nm[a], nm[b], m)]; }
-        for (int b = 0; b < o; b++) for (int a = 0; a < b; a++) { double v = (S[IX(a, b, o)] + S[IX(b, a, o)]) / 2; S[IX(a, b, o)] = v; S[IX(b, a, o)] = v; }
-        double det = lu_inv_det(o, S, Sinv);
-        for (int b = 0; b < o; b++) for (int i = 0; i < n; i++) { double a = 0; for (int k = 0; k < o; k++) a += C[IX(i, k, n)] * Sinv[IX(k, b, o)]; K[IX(i, b, n)] = a; }   // computeK_C
-        for (int i = 0; i < n; i++) { double a = 0; for (int b = 0; b < o; b++) a += K[IX(i, b, n)] * res[b]; mvec[i] = m_[i] + a; }
-        double KS[NMAX * MMAX];                                                       // updateP_C (Internals.h:99-101) + symmetrise (:809)
-        for (int b = 0; b < o; b++) for (int i = 0; i < n; i++) { double a = 0; for (int k = 0; k < o; k++) a += K[IX(i, k, n)] * S[IX(k, b, o)]; KS[IX(i, b, n)] = a; }
-        for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) { double a = 0; for (int k = 0; k < o; k++) a += KS[IX(i, k, n)] * K[IX(j, k, n)]; P[IX(i, j, n)] = P_[IX(i, j, n)] - a; }
-        for (int j = 0; j < n; j++) for (int i = 0; i < j; i++) { double v = (P[IX(i, j, n)] + P[IX(j, i, n)]) / 2; P[IX(i, j, n)] = v; P[IX(j, i, n)] = v; }
-        double z[MMAX], dist = 0;                                                     // computeIndividualM2LL_C (Internals.h:103-115)
-        for (int a = 0; a < o; a++) { double acc = 0; for (int k = 0; k < o; k++) acc += Sinv[IX(a, k, o)] * res[k]; z[a] = acc; }
+        real YW[MMAX * SMAX];
+        for (int co = 0; co < s; co++) for (int a = 0; a < o; a++) { real acc = 0; for (int k = 0; k < s; k++) acc += Yo[IX(a, k, o)] * W[IX(k, co, s)]; YW[IX(a, co, o)] = acc; }
+        for (int b = 0; b < o; b++) for (int a = 0; a < o; a++) { real acc = 0; for (int k = 0; k < s; k++) acc += YW[IX(a, k, o)] * Yo[IX(b, k, o)]; S[IX(a, b, o)] = acc + Rfull[IX(nm[a], nm[b], m)]; }
+        for (int b = 0; b < o; b++) for (int a = 0; a < b; a++) { real v = (S[IX(a, b, o)] + S[IX(b, a, o)]) / 2; S[IX(a, b, o)] = v; S[IX(b, a, o)] = v; }
+        real det = lu_inv_det(o, S, Sinv);
+        for (int b = 0; b < o; b++) for (int i = 0; i < n; i++) { real a = 0; for (int k = 0; k < o; k++) a += C[IX(i, k, n)] * Sinv[IX(k, b, o)]; K[IX(i, b, n)] = a; }   // computeK_C
+        for (int i = 0; i < n; i++) { real a = 0; for (int b = 0; b < o; b++) a += K[IX(i, b, n)] * res[b]; mvec[i] = m_[i] + a; }
+        real KS[NMAX * MMAX];                                                       // updateP_C (Internals.h:99-101) + symmetrise (:809)
+        for (int b = 0; b < o; b++) for (int i = 0; i < n; i++) { real a = 0; for (int k = 0; k < o; k++) a += K[IX(i, k, n)] * S[IX(k, b, o)]; KS[IX(i, b, n)] = a; }
+        for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) { real a = 0; for (int k = 0; k < o; k++) a += KS[IX(i, k, n)] * K[IX(j, k, n)]; P[IX(i, j, n)] = P_[IX(i, j, n)] - a; }
+        for (int j = 0; j < n; j++) for (int i = 0; i < j; i++) { real v = (P[IX(i, j, n)] + P[IX(j, i, n)]) / 2; P[IX(i, j, n)] = v; P[IX(j, i, n)] = v; }
+        real z[MMAX], dist = 0;                                                     // computeIndividualM2LL_C (Internals.h:103-115)
+        for (int a = 0; a < o; a++) { real acc = 0; for (int k = 0; k < o; k++) acc += Sinv[IX(a, k, o)] * res[k]; z[a] = acc; }
         for (int a = 0; a < o; a++) dist += res[a] * z[a];
         m2ll += o * std::log(2 * M_PI) + std::log(det) + dist;
       }
-      if (latent) for (int i = 0; i < n; i++) latent[(size_t)tp * n + i] = mvec[i];   // :379
+      if (latent) for (int i = 0; i < n; i++) latent[(size_t)tp * n + i] = (double)mvec[i];   // :379
     } else {
       for (int i = 0; i < n; i++) mvec[i] = m_[i];                                   // :404-408
-      if (latent) for (int i = 0; i < n; i++) latent[(size_t)tp * n + i] = mvec[i];
+      if (latent) for (int i = 0; i < n; i++) latent[(size_t)tp * n + i] = (double)mvec[i];
       if (!st.sr) {                                                                   // :832-834
-        for (int j = 0; j < n; j++) for (int i = 0; i <= j; i++) { double v = (P_[IX(i, j, n)] + P_[IX(j, i, n)]) / 2; P[IX(i, j, n)] = v; P[IX(j, i, n)] = v; }
+        for (int j = 0; j < n; j++) for (int i = 0; i <= j; i++) { real v = (P_[IX(i, j, n)] + P_[IX(j, i, n)]) / 2; P[IX(i, j, n)] = v; P[IX(j, i, n)] = v; }
       }
     }
   }
@@ -487,27 +492,27 @@ double fit_person(const Settings& st, user_fn drift, user_fn meas, const double*
 struct Problem {
   Settings st; user_fn drift, meas;
   int N, F, P;
-  const double* base_plist;     // plist_len
+  const double* base_plist;   // plist_len
   const int* slot_off;          // F: flat offset of free slot k inside plist
   const int* theta_index;       // N x F row-major
   const int64_t* row_off;       // N+1
-  const double* obs;            // rows x m ROW-major
-  const double* dt;             // rows
+  const double* obs;          // rows x m ROW-major
+  const double* dt;           // rows
   const int* person_id;         // N
 };
 
 // Stateless parameter semantics (quirk Q4): base values overwritten by THIS person's theta entries
 // (setParameterList_C, inst/include/psydiffBasic.h:63-121, with every row flagged changed).
-void person_plist(const Problem& pb, const double* theta, int p, double* plist) {
-  std::memcpy(plist, pb.base_plist, sizeof(double) * pb.st.plist_len);
+void person_plist(const Problem& pb, const double* theta, int p, real* plist) {
+  for (int i = 0; i < pb.st.plist_len; i++) plist[i] = pb.base_plist[i];
   for (int k = 0; k < pb.F; k++) plist[pb.slot_off[k]] = theta[pb.theta_index[(size_t)p * pb.F + k]];
 }
 
 double fit_one(const Problem& pb, const double* theta, int p, double* latent, double* pred) {
-  std::vector<double> plist(pb.st.plist_len);
+  std::vector<real> plist(pb.st.plist_len);
   person_plist(pb, theta, p, plist.data());
   int64_t r0 = pb.row_off[p]; int T = (int)(pb.row_off[p + 1] - r0);
-  return fit_person(pb.st, pb.drift, pb.meas, plist.data(), pb.person_id[p], T, pb.obs + r0 * pb.st.m, pb.dt + r0,
+  return (double)fit_person(pb.st, pb.drift, pb.meas, plist.data(), pb.person_id[p], T, pb.obs + r0 * pb.st.m, pb.dt + r0,
                     latent ? latent + r0 * pb.st.n : nullptr, pred ? pred + r0 * pb.st.m : nullptr);
 }
 
@@ -612,6 +617,7 @@ unsigned long long psy_oracle_flops_reset(void) {
 #endif
 }
 
+#ifndef PSY_EXT  // the primitive wrappers exist in the double build only
 // ---- primitives, for unit tests of the oracle itself (src/exposeInlineFunctions.cpp names) ----
 void psy_oracle_getMeanWeights(int n, double alpha, double beta, double kappa, double* wm) { double wc[SMAX]; ut_weights(n, alpha, beta, kappa, wm, wc); }
 void psy_oracle_getCovWeights(int n, double alpha, double beta, double kappa, double* wc) { double wm[SMAX]; ut_weights(n, alpha, beta, kappa, wm, wc); }
@@ -628,5 +634,7 @@ double psy_oracle_computeIndividualM2LL(int o, const double* raw, const double* 
   for (int a = 0; a < o; a++) dist += res[a] * z[a];
   return o * std::log(2 * M_PI) + std::log(det) + dist;
 }
+
+#endif
 
 }  // extern "C"

@@ -7,38 +7,43 @@
 #pragma once
 #include <cmath>
 
+#ifndef PSY_REAL
+#define PSY_REAL double
+#endif
+typedef PSY_REAL real;
+
 namespace ol {
 
 struct Mat;
 constexpr int VCAP = 16, MCAP = 256;  // inline storage: no heap traffic in the hot loop
 
 struct Vec {
-  double v[VCAP];
+  real v[VCAP];
   int len = 0;
   Vec() {}
   explicit Vec(int n) : len(n) { for (int i = 0; i < n; i++) v[i] = 0.0; }
-  Vec(const double* p, int n) : len(n) { for (int i = 0; i < n; i++) v[i] = p[i]; }
-  double& operator()(int i) { return v[i]; }
-  const double& operator()(int i) const { return v[i]; }
-  double& operator[](int i) { return v[i]; }
-  const double& operator[](int i) const { return v[i]; }
+  Vec(const real* p, int n) : len(n) { for (int i = 0; i < n; i++) v[i] = p[i]; }
+  real& operator()(int i) { return v[i]; }
+  const real& operator()(int i) const { return v[i]; }
+  real& operator[](int i) { return v[i]; }
+  const real& operator[](int i) const { return v[i]; }
   int n() const { return len; }
-  Vec& operator=(double s) { len = 1; v[0] = s; return *this; }  // arma: scalar assignment makes a 1x1 object
+  Vec& operator=(real s) { len = 1; v[0] = s; return *this; }  // arma: scalar assignment makes a 1x1 object
 };
 
 struct Mat {
   int r = 0, c = 0;
-  double a[MCAP];  // column-major
+  real a[MCAP];  // column-major
   Mat() {}
   Mat(int r_, int c_) : r(r_), c(c_) { for (int i = 0; i < r_ * c_; i++) a[i] = 0.0; }
-  Mat(const double* p, int r_, int c_) : r(r_), c(c_) { for (int i = 0; i < r_ * c_; i++) a[i] = p[i]; }
+  Mat(const real* p, int r_, int c_) : r(r_), c(c_) { for (int i = 0; i < r_ * c_; i++) a[i] = p[i]; }
   int size() const { return r * c; }
-  double& operator()(int i, int j) { return a[i + (size_t)j * r]; }
-  const double& operator()(int i, int j) const { return a[i + (size_t)j * r]; }
-  double& operator()(int i) { return a[i]; }
-  const double& operator()(int i) const { return a[i]; }
-  double& operator[](int i) { return a[i]; }
-  const double& operator[](int i) const { return a[i]; }
+  real& operator()(int i, int j) { return a[i + (size_t)j * r]; }
+  const real& operator()(int i, int j) const { return a[i + (size_t)j * r]; }
+  real& operator()(int i) { return a[i]; }
+  const real& operator()(int i) const { return a[i]; }
+  real& operator[](int i) { return a[i]; }
+  const real& operator[](int i) const { return a[i]; }
 };
 
 inline Vec operator+(const Vec& a, const Vec& b) { Vec r(a.n()); for (int i = 0; i < a.n(); i++) r.v[i] = a.v[i] + b.v[i]; return r; }
@@ -49,26 +54,26 @@ inline Vec operator+(const Mat& a, const Vec& b) { Vec r(b.n()); for (int i = 0;
 inline Vec operator+(const Vec& a, const Mat& b) { Vec r(a.n()); for (int i = 0; i < a.n(); i++) r.v[i] = a.v[i] + b.a[i]; return r; }
 inline Vec operator-(const Mat& a, const Vec& b) { Vec r(b.n()); for (int i = 0; i < b.n(); i++) r.v[i] = a.a[i] - b.v[i]; return r; }
 inline Vec operator-(const Vec& a, const Mat& b) { Vec r(a.n()); for (int i = 0; i < a.n(); i++) r.v[i] = a.v[i] - b.a[i]; return r; }
-inline Vec operator*(double s, const Vec& a) { Vec r(a.n()); for (int i = 0; i < a.n(); i++) r.v[i] = s * a.v[i]; return r; }
-inline Vec operator*(const Vec& a, double s) { return s * a; }
-inline Vec operator/(const Vec& a, double s) { Vec r(a.n()); for (int i = 0; i < a.n(); i++) r.v[i] = a.v[i] / s; return r; }
-inline Vec operator+(const Vec& a, double s) { Vec r(a.n()); for (int i = 0; i < a.n(); i++) r.v[i] = a.v[i] + s; return r; }
-inline Vec operator+(double s, const Vec& a) { return a + s; }
-inline Vec operator-(const Vec& a, double s) { Vec r(a.n()); for (int i = 0; i < a.n(); i++) r.v[i] = a.v[i] - s; return r; }
+inline Vec operator*(real s, const Vec& a) { Vec r(a.n()); for (int i = 0; i < a.n(); i++) r.v[i] = s * a.v[i]; return r; }
+inline Vec operator*(const Vec& a, real s) { return s * a; }
+inline Vec operator/(const Vec& a, real s) { Vec r(a.n()); for (int i = 0; i < a.n(); i++) r.v[i] = a.v[i] / s; return r; }
+inline Vec operator+(const Vec& a, real s) { Vec r(a.n()); for (int i = 0; i < a.n(); i++) r.v[i] = a.v[i] + s; return r; }
+inline Vec operator+(real s, const Vec& a) { return a + s; }
+inline Vec operator-(const Vec& a, real s) { Vec r(a.n()); for (int i = 0; i < a.n(); i++) r.v[i] = a.v[i] - s; return r; }
 inline Vec operator-(const Vec& a) { Vec r(a.n()); for (int i = 0; i < a.n(); i++) r.v[i] = -a.v[i]; return r; }
 inline Mat operator+(const Mat& a, const Mat& b) { Mat r(a.r, a.c); for (int i = 0; i < a.size(); i++) r.a[i] = a.a[i] + b.a[i]; return r; }
 inline Mat operator-(const Mat& a, const Mat& b) { Mat r(a.r, a.c); for (int i = 0; i < a.size(); i++) r.a[i] = a.a[i] - b.a[i]; return r; }
-inline Mat operator*(double s, const Mat& a) { Mat r(a.r, a.c); for (int i = 0; i < a.size(); i++) r.a[i] = s * a.a[i]; return r; }
-inline Mat operator*(const Mat& a, double s) { return s * a; }
+inline Mat operator*(real s, const Mat& a) { Mat r(a.r, a.c); for (int i = 0; i < a.size(); i++) r.a[i] = s * a.a[i]; return r; }
+inline Mat operator*(const Mat& a, real s) { return s * a; }
 inline Mat operator-(const Mat& a) { return -1.0 * a; }
 inline Vec operator*(const Mat& A, const Vec& x) {
   Vec r(A.r);
-  for (int i = 0; i < A.r; i++) { double acc = 0; for (int k = 0; k < A.c; k++) acc += A(i, k) * x.v[k]; r.v[i] = acc; }
+  for (int i = 0; i < A.r; i++) { real acc = 0; for (int k = 0; k < A.c; k++) acc += A(i, k) * x.v[k]; r.v[i] = acc; }
   return r;
 }
 inline Mat operator*(const Mat& A, const Mat& B) {
   Mat r(A.r, B.c);
-  for (int j = 0; j < B.c; j++) for (int i = 0; i < A.r; i++) { double acc = 0; for (int k = 0; k < A.c; k++) acc += A(i, k) * B(k, j); r(i, j) = acc; }
+  for (int j = 0; j < B.c; j++) for (int i = 0; i < A.r; i++) { real acc = 0; for (int k = 0; k < A.c; k++) acc += A(i, k) * B(k, j); r(i, j) = acc; }
   return r;
 }
 }  // namespace ol
@@ -76,8 +81,8 @@ inline Mat operator*(const Mat& A, const Mat& B) {
 namespace arma {
 inline ol::Vec exp(const ol::Vec& a) { ol::Vec r(a.n()); for (int i = 0; i < a.n(); i++) r.v[i] = std::exp(a.v[i]); return r; }
 inline ol::Vec log(const ol::Vec& a) { ol::Vec r(a.n()); for (int i = 0; i < a.n(); i++) r.v[i] = std::log(a.v[i]); return r; }
-inline double dot(const ol::Vec& a, const ol::Vec& b) { double s = 0; for (int i = 0; i < a.n(); i++) s += a.v[i] * b.v[i]; return s; }
-inline double accu(const ol::Vec& a) { double s = 0; for (int i = 0; i < a.n(); i++) s += a.v[i]; return s; }
-inline double sum(const ol::Vec& a) { return accu(a); }
+inline real dot(const ol::Vec& a, const ol::Vec& b) { real s = 0; for (int i = 0; i < a.n(); i++) s += a.v[i] * b.v[i]; return s; }
+inline real accu(const ol::Vec& a) { real s = 0; for (int i = 0; i < a.n(); i++) s += a.v[i]; return s; }
+inline real sum(const ol::Vec& a) { return accu(a); }
 inline ol::Mat trans(const ol::Mat& a) { ol::Mat r(a.c, a.r); for (int j = 0; j < a.c; j++) for (int i = 0; i < a.r; i++) r(j, i) = a(i, j); return r; }
 }  // namespace arma

@@ -43,6 +43,10 @@ SIGNATURES = {
     "psy_grad_level": (C.c_int, [C.c_void_p, c_double_p, C.c_double, C.c_int, c_ubyte_p, C.POINTER(C.c_void_p)]),
     "psy_grad_resolve": (C.c_int, [C.c_void_p, c_double_p, C.c_double, C.c_int, C.c_int, C.c_int, c_ubyte_p, c_int_p]),
     "psy_grad_finish": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p]),
+    "psy_sweep_create": (C.c_void_p, [C.c_int]),
+    "psy_sweep_destroy": (None, [C.c_void_p]),
+    "psy_sweep_resolve": (C.c_int, [C.c_void_p, c_double_p, C.c_double, C.c_int, C.c_int, C.c_int, c_ubyte_p, c_int_p]),
+    "psy_sweep_finish": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p]),
     "psy_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "psy_last_kernel_instances": (C.c_int64, [C.c_void_p]),
     "psy_launch_count": (C.c_int64, []),

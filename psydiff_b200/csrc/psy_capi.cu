@@ -16,6 +16,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -114,6 +115,16 @@ struct Chunk { int theta; int start; int len; int pad; };
 
 }  // namespace
 
+// host-only bookkeeping of one finite-difference sweep (the eps[] fallback of R/modelTemplate.R:885-898, 905-919)
+struct psy_sweep {
+  int P = 0;
+  double base_total = 0.0, base_nonfinite = 0.0;
+  std::vector<double> Dval;             // [P*2]  Σ_p (f_side − f0)
+  std::vector<double> eps_used;         // [P]
+  std::vector<unsigned char> resolved;  // [P*2]
+  std::vector<unsigned char> wanted;    // [P*2]
+};
+
 struct psy_model {
   int n = 0, m = 0, F = 0, P = 0, N = 0;
   int64_t rows = 0;
@@ -124,6 +135,7 @@ struct psy_model {
   // module
   CUmodule mod = nullptr;
   CUfunction fn = nullptr;
+  int block = 128;  // = the module's __launch_bounds__ block size
   // host copies
   std::vector<double> h_dt;
   std::vector<int64_t> h_row_off;
@@ -144,12 +156,9 @@ struct psy_model {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0.0;
   int64_t last_instances = 0;
-  // gradient sweep state (psy_grad_resolve)
-  double base_total = 0.0, base_nonfinite = 0.0;
-  std::vector<double> Dval;      // [P*2]
-  std::vector<double> eps_used;  // [P]
-  std::vector<unsigned char> resolved;  // [P*2]
-  std::vector<unsigned char> wanted;    // [P*2] sides the current sweep asks for
+  psy_sweep sweep;  // gradient sweep state (psy_grad_resolve)
+  double* stage = nullptr;  // pinned staging buffer for psy_upload
+  size_t stage_n = 0;
 };
 
 // =================================================================================================================
@@ -310,7 +319,7 @@ int launch_filter(psy_model* M, const PsyInst* d_list, const int* d_out_idx, int
   L.wc1 = L.wm1;
   L.n_inst = (int)count;
   L.skip_update = skip_update;
-  const unsigned block = 128;
+  const unsigned block = (unsigned)M->block;
   const unsigned grid = (unsigned)((count + block - 1) / block);
   void* args[] = {&L};
   CU_TRY(cudaEventRecord(M->ev0, 0));
@@ -400,6 +409,8 @@ psy_model* psy_model_create(int n, int m, int nfree, const char* cubin_path) {
   if (r != CUDA_SUCCESS) { fail(PSY_ERR_CUDA, "cuModuleLoadData(%s): %s", cubin_path, cu_str(r)); delete M; return nullptr; }
   r = g_drv.ModuleGetFunction(&M->fn, M->mod, "psy_filter_kernel");
   if (r != CUDA_SUCCESS) { fail(PSY_ERR_CUDA, "psy_filter_kernel not found in %s: %s", cubin_path, cu_str(r)); g_drv.ModuleUnload(M->mod); delete M; return nullptr; }
+  int mt = 0;
+  if (g_drv.FuncGetAttribute(&mt, CU_FUNC_ATTRIBUTE_MAX_THREADS_PER_BLOCK, M->fn) == CUDA_SUCCESS && mt >= 32 && mt <= 256) M->block = mt;
   cudaEventCreate(&M->ev0);
   cudaEventCreate(&M->ev1);
   return M;
@@ -411,6 +422,7 @@ void psy_model_destroy(psy_model* M) {
   M->d_chunk_part.release(); M->d_partial.release(); M->d_ksteps.release(); M->d_pid.release(); M->d_tidx.release();
   M->d_pair_minus.release(); M->d_pair_base.release(); M->d_out_idx.release(); M->d_theta_chunk_off.release();
   M->d_row_off.release(); M->d_inst.release(); M->d_inst_sub.release(); M->d_inst_base.release(); M->d_chunks.release();
+  if (M->stage) cudaFreeHost(M->stage);
   if (M->ev0) cudaEventDestroy(M->ev0);
   if (M->ev1) cudaEventDestroy(M->ev1);
   if (M->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(M->mod);
@@ -431,21 +443,37 @@ int psy_upload(psy_model* M, int64_t rows, int N, const double* obs_cm, const do
   for (int p = 0; p < N; p++)
     if (person_off[p + 1] <= person_off[p]) return fail(PSY_ERR_ARG, "psy_upload: person %d has no rows", p);
   const int m = M->m;
-  // R's column-major rows x m  ->  row-major [rows][m], so one time point is m contiguous doubles in HBM
-  std::vector<double> rm((size_t)rows * m);
-  for (int j = 0; j < m; j++)
-    for (int64_t r = 0; r < rows; r++) rm[(size_t)r * m + j] = obs_cm[(size_t)j * rows + r];
+  // R's column-major rows x m  ->  row-major [rows][m], so one time point is m contiguous doubles in HBM.
+  // The transpose goes through a pinned staging buffer so the H2D copy runs at full PCIe/C2C rate.
+  const size_t cnt = (size_t)rows * m;
+  if (M->stage_n < cnt) {
+    if (M->stage) cudaFreeHost(M->stage);
+    M->stage = nullptr; M->stage_n = 0;
+    CU_TRY(cudaMallocHost((void**)&M->stage, cnt * sizeof(double)));
+    M->stage_n = cnt;
+  }
+  double* rm = M->stage;
+  const int64_t RB = 4096;
+  for (int64_t r0 = 0; r0 < rows; r0 += RB) {
+    const int64_t r1 = std::min(rows, r0 + RB);
+    for (int j = 0; j < m; j++) {
+      const double* col = obs_cm + (size_t)j * rows;
+      for (int64_t r = r0; r < r1; r++) rm[(size_t)r * m + j] = col[r];
+    }
+  }
   int rc;
-  if ((rc = M->d_obs.upload(rm.data(), rm.size()))) return rc;
+  if ((rc = M->d_obs.upload(rm, cnt))) return rc;
   if ((rc = M->d_dt.upload(dt, rows))) return rc;
   std::vector<long long> ro(person_off, person_off + N + 1);
   if ((rc = M->d_row_off.upload(ro.data(), ro.size()))) return rc;
   if ((rc = M->d_pid.upload(person_id, N))) return rc;
   M->h_dt.assign(dt, dt + rows);
   M->h_row_off.assign(person_off, person_off + N + 1);
+  if (N != M->N) {  // a dataset with a different person count invalidates the slot map
+    M->d_tidx.release();
+    M->n_inst = 0;
+  }
   M->rows = rows; M->N = N; M->ksteps_h = -1.0;
-  M->d_tidx.release();  // a new dataset invalidates the slot map
-  M->n_inst = 0;
   return PSY_OK;
 }
 
@@ -592,23 +620,31 @@ int psy_grad_level(psy_model* M, const double* theta, double eps, int direction,
   return PSY_OK;
 }
 
-int psy_grad_resolve(psy_model* M, const double* part, double eps, int level, int n_eps, int direction, unsigned char* need, int* done) {
-  if (!M || !part || !need || !done) return fail(PSY_ERR_ARG, "psy_grad_resolve: bad arguments");
-  const int P = M->P;
+psy_sweep* psy_sweep_create(int n_theta) {
+  if (n_theta < 0) { fail(PSY_ERR_ARG, "psy_sweep_create: bad arguments"); return nullptr; }
+  psy_sweep* S = new psy_sweep;
+  S->P = n_theta;
+  return S;
+}
+void psy_sweep_destroy(psy_sweep* S) { delete S; }
+
+int psy_sweep_resolve(psy_sweep* S, const double* part, double eps, int level, int n_eps, int direction, unsigned char* need, int* done) {
+  if (!S || !part || !need || !done) return fail(PSY_ERR_ARG, "psy_sweep_resolve: bad arguments");
+  if (direction < 0 || direction > 2) return fail(PSY_ERR_ARG, "Unknown direction argument. Possible are central, left and right");
+  const int P = S->P;
   if (level == 0) {
-    M->base_total = part[0];
-    M->base_nonfinite = part[1];
-    M->Dval.assign((size_t)P * 2, 0.0);
-    M->eps_used.assign(P, 0.0);
-    M->resolved.assign((size_t)P * 2, 0);
-    if (M->wanted.size() != (size_t)P * 2) {
-      M->wanted.assign((size_t)P * 2, 0);
-      for (int t = 0; t < P; t++) {
-        M->wanted[2 * t + 0] = (direction == PSY_DIR_CENTRAL || direction == PSY_DIR_LEFT);
-        M->wanted[2 * t + 1] = (direction == PSY_DIR_CENTRAL || direction == PSY_DIR_RIGHT);
-      }
+    S->base_total = part[0];
+    S->base_nonfinite = part[1];
+    S->Dval.assign((size_t)P * 2, 0.0);
+    S->eps_used.assign(P, 0.0);
+    S->resolved.assign((size_t)P * 2, 0);
+    S->wanted.assign((size_t)P * 2, 0);
+    for (int t = 0; t < P; t++) {
+      S->wanted[2 * t + 0] = (direction == PSY_DIR_CENTRAL || direction == PSY_DIR_LEFT);
+      S->wanted[2 * t + 1] = (direction == PSY_DIR_CENTRAL || direction == PSY_DIR_RIGHT);
     }
   }
+  if (S->wanted.size() != (size_t)P * 2) return fail(PSY_ERR_STATE, "psy_sweep_resolve: level 0 has not been resolved");
   const double* Dp = part + 2;
   const double* Dm = part + 2 + (size_t)P;
   const double* nfp = part + 2 + 2 * (size_t)P;
@@ -619,15 +655,15 @@ int psy_grad_resolve(psy_model* M, const double* part, double eps, int level, in
     for (int side = 0; side < 2; side++) {
       const size_t k = 2 * (size_t)t + side;
       need[k] = 0;
-      if (!M->wanted[k] || M->resolved[k]) continue;
+      if (!S->wanted[k] || S->resolved[k]) continue;
       const double D = side ? Dp[t] : Dm[t];
       const double nf = side ? nfp[t] : nfm[t];
       // Σ -2LL over ALL persons is finite  <=>  untouched persons finite at base, touched persons finite here
-      const bool ok = (M->base_nonfinite - nbt[t] == 0.0) && nf == 0.0 && std::isfinite(D);
+      const bool ok = (S->base_nonfinite - nbt[t] == 0.0) && nf == 0.0 && std::isfinite(D);
       if (ok) {
-        M->resolved[k] = 1;
-        M->Dval[k] = D;
-        M->eps_used[t] += eps;  // R/modelTemplate.R:893, 914
+        S->resolved[k] = 1;
+        S->Dval[k] = D;
+        S->eps_used[t] += eps;  // R/modelTemplate.R:893, 914
       } else if (level + 1 < n_eps) {
         need[k] = 1;
         pending++;
@@ -638,19 +674,31 @@ int psy_grad_resolve(psy_model* M, const double* part, double eps, int level, in
   return PSY_OK;
 }
 
-int psy_grad_finish(psy_model* M, int direction, double* grad, double* total) {
-  if (!M || !grad) return fail(PSY_ERR_ARG, "psy_grad_finish: bad arguments");
+int psy_sweep_finish(psy_sweep* S, int direction, double* grad, double* total) {
+  if (!S || !grad) return fail(PSY_ERR_ARG, "psy_sweep_finish: bad arguments");
+  if (S->wanted.size() != (size_t)S->P * 2) return fail(PSY_ERR_STATE, "psy_sweep_finish: nothing resolved");
+  (void)direction;
   const double nan = std::nan("");
-  for (int t = 0; t < M->P; t++) {
-    const bool wl = M->wanted[2 * t], wr = M->wanted[2 * t + 1];
-    if ((wl && !M->resolved[2 * t]) || (wr && !M->resolved[2 * t + 1]) || (!wl && !wr)) { grad[t] = nan; continue; }
-    if (!(wl && wr) && M->base_nonfinite != 0.0) { grad[t] = nan; continue; }  // one-sided: the other side is Σ f0
-    const double dplus = wr ? M->Dval[2 * t + 1] : 0.0, dminus = wl ? M->Dval[2 * t] : 0.0;
-    grad[t] = (dplus - dminus) / M->eps_used[t];  // R/modelTemplate.R:926
+  for (int t = 0; t < S->P; t++) {
+    const bool wl = S->wanted[2 * t], wr = S->wanted[2 * t + 1];
+    if ((wl && !S->resolved[2 * t]) || (wr && !S->resolved[2 * t + 1]) || (!wl && !wr)) { grad[t] = nan; continue; }
+    if (!(wl && wr) && S->base_nonfinite != 0.0) { grad[t] = nan; continue; }  // one-sided: the other side is Σ f0
+    const double dplus = wr ? S->Dval[2 * t + 1] : 0.0, dminus = wl ? S->Dval[2 * t] : 0.0;
+    grad[t] = (dplus - dminus) / S->eps_used[t];  // R/modelTemplate.R:926
   }
-  if (total) *total = M->base_total;
-  M->wanted.clear();
+  if (total) *total = S->base_total;
   return PSY_OK;
+}
+
+int psy_grad_resolve(psy_model* M, const double* part, double eps, int level, int n_eps, int direction, unsigned char* need, int* done) {
+  if (!M) return fail(PSY_ERR_ARG, "psy_grad_resolve: bad arguments");
+  M->sweep.P = M->P;
+  return psy_sweep_resolve(&M->sweep, part, eps, level, n_eps, direction, need, done);
+}
+
+int psy_grad_finish(psy_model* M, int direction, double* grad, double* total) {
+  if (!M) return fail(PSY_ERR_ARG, "psy_grad_finish: bad arguments");
+  return psy_sweep_finish(&M->sweep, direction, grad, total);
 }
 
 static int grad_sweep(psy_model* M, const double* theta, const double* eps, int n_eps, int direction, double* grad, double* total) {
@@ -659,7 +707,6 @@ static int grad_sweep(psy_model* M, const double* theta, const double* eps, int 
   const int P = M->P;
   std::vector<unsigned char> need((size_t)P * 2 + 1, 0);
   std::vector<double> part((size_t)psy_partial_len(M));
-  M->wanted.clear();
   int done = 0, rc;
   for (int level = 0; level < n_eps && !done; level++) {
     void* dptr = nullptr;

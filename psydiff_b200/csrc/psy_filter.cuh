@@ -34,6 +34,9 @@
 #ifndef PSY_BLOCK
 #define PSY_BLOCK 128
 #endif
+#ifndef PSY_MIN_BLOCKS
+#define PSY_MIN_BLOCKS 1
+#endif
 
 namespace psy {
 
@@ -82,9 +85,8 @@ struct Filter {
 #pragma unroll
       for (int i = 0; i < N; i++) {
         if (i >= j) {
-          double d = ut.sqrtc * A[tri(i, j)];
-          xp.v[i] = m[i] + d;
-          xm.v[i] = m[i] - d;
+          xp.v[i] = fma(ut.sqrtc, A[tri(i, j)], m[i]);
+          xm.v[i] = fma(-ut.sqrtc, A[tri(i, j)], m[i]);
         } else {
           xp.v[i] = m[i];
           xm.v[i] = m[i];
@@ -484,6 +486,6 @@ struct Filter {
 }  // namespace psy
 
 #define PSY_INSTANTIATE(MODEL)                                                                  \
-  extern "C" __global__ void __launch_bounds__(PSY_BLOCK) psy_filter_kernel(const PsyLaunch L) { \
+  extern "C" __global__ void __launch_bounds__(PSY_BLOCK, PSY_MIN_BLOCKS) psy_filter_kernel(const PsyLaunch L) { \
     psy::Filter<MODEL>::run(L);                                                                 \
   }

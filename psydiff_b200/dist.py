@@ -1,0 +1,102 @@
+"""Multi-GPU evaluation: persons are sharded over ranks (one process per GPU), each rank filters its own persons and
+the per-parameter partial sums are combined with ONE all-reduce per eps level (NCCL over NVLink on the device buffer).
+
+This replaces the reference's only parallel path — getGradientsParallel's PSOCK workers, which ship the whole model
+including the data to every worker on every call (R/prepareModel.R:608-616).  Persons are independent units
+(R/modelTemplate.R:244), so there is no data-path collective; the all-reduce carries 5P+2 doubles.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _lib
+from .model import _direction, _push_settings
+
+
+class _DevVec:
+    """Zero-copy view of a device buffer owned by libpsydiff_b200 (consumed by torch.as_tensor)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def shard_bounds(n_persons: int, world: int):
+    """Contiguous person blocks per rank (balanced by count; equal T and P_i make that balanced by work as well)."""
+    b = [(n_persons * r) // world for r in range(world + 1)]
+    return [(b[r], b[r + 1]) for r in range(world)]
+
+
+def allreduce_partial(partial_ptr: int, n: int, group=None) -> np.ndarray:
+    """Sum the device-resident partial vector across ranks and return the reduced vector on the host."""
+    import torch
+    import torch.distributed as dist
+    t = torch.as_tensor(_DevVec(partial_ptr, n), device="cuda")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
+def getGradientsSharded(psydiffModel, group=None, return_total: bool = False):
+    """getGradients over person shards: every rank passes its own shard's model (same parameters, same labels).
+    Returns the full gradient (identical on every rank)."""
+    L = _lib.lib()
+    h = _push_settings(psydiffModel)
+    pt = psydiffModel["pars"]["parameterTable"]
+    theta = np.ascontiguousarray(pt.theta_values, dtype=np.float64)
+    eps = np.ascontiguousarray(psydiffModel["eps"], dtype=np.float64)
+    direction = _direction(psydiffModel)
+    P = len(theta)
+    n = int(L.psy_partial_len(h.ptr))
+    need = np.zeros(2 * P + 1, dtype=np.uint8)
+    done = C.c_int(0)
+    for level in range(len(eps)):
+        dptr = C.c_void_p()
+        _lib.check(L.psy_grad_level(h.ptr, _lib.dptr(theta), float(eps[level]), direction,
+                                    None if level == 0 else _lib.u8ptr(need), C.byref(dptr)))
+        part = np.ascontiguousarray(allreduce_partial(dptr.value, n, group))
+        _lib.check(L.psy_grad_resolve(h.ptr, _lib.dptr(part), float(eps[level]), level, len(eps), direction,
+                                      _lib.u8ptr(need), C.byref(done)))
+        if done.value:
+            break
+    g = np.empty(P)
+    tot = C.c_double(0.0)
+    _lib.check(L.psy_grad_finish(h.ptr, direction, _lib.dptr(g), C.byref(tot)))
+    out: Dict[str, float] = {l: float(v) for l, v in zip(pt.theta_labels, g)}
+    return (out, tot.value) if return_total else out
+
+
+def merge_labels(label_lists, value_lists):
+    """Global theta = shard label lists concatenated in rank order, first appearance wins.  Because shards are contiguous
+    person blocks in dataset order, this IS the first-appearance order of the unsharded parameterTable."""
+    labels, values, pos = [], [], {}
+    for ll, vv in zip(label_lists, value_lists):
+        for l, v in zip(ll, vv):
+            if l not in pos:
+                pos[l] = len(labels)
+                labels.append(l)
+                values.append(float(v))
+    return labels, np.asarray(values, dtype=float), pos
+
+
+def align_parameters(psydiffModel, label_lists=None, value_lists=None, group=None):
+    """Give every rank's shard model the same theta vector (labels, order, length): gathers the shards' label lists,
+    merges them and re-indexes this shard's slot map.  Parameters no person of this shard carries simply have no
+    instances here.  Must be called before compileModel (the slot map is uploaded there)."""
+    pt = psydiffModel["pars"]["parameterTable"]
+    if label_lists is None:
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (list(pt.theta_labels), [float(v) for v in pt.theta_values]), group=group)
+        label_lists = [g[0] for g in gathered]
+        value_lists = [g[1] for g in gathered]
+    labels, values, pos = merge_labels(label_lists, value_lists)
+    remap = np.asarray([pos[l] for l in pt.theta_labels], dtype=np.int32)
+    pt.theta_index = np.ascontiguousarray(remap[pt.theta_index], dtype=np.int32)
+    pt.theta_labels = labels
+    pt.theta_values = values
+    pt._label_pos = pos
+    return psydiffModel

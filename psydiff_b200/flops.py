@@ -1,0 +1,99 @@
+"""Flop accounting for the filter kernel (FMA = 2 flops; a reciprocal, sqrt, exp or log counts 1).
+
+``kernel_flops``  — the arithmetic the kernel's reduced (m, A) formulation executes per RK4 step / per update, counted by
+                    walking the same loop nests as psy_filter.cuh (checked against ncu's DADD/DMUL/DFMA instruction
+                    counters, profiles/).  This is the figure bench.py's roofline uses: it is what the FP64 pipe must do.
+``survey_flops``  — SURVEY.md §8(d)'s closed form for the reference's full-sigma-matrix formulation, reported beside it.
+"""
+from __future__ import annotations
+
+
+def rhs_flops(n: int, Ff: int, l_diag: bool = True) -> int:
+    tn = n * (n + 1) // 2
+    f = n  # reciprocals of the diagonal
+    for j in range(n):          # explicit triangular inverse
+        for i in range(j + 1, n):
+            f += 1 + 2 * (i - j - 1) + 1
+    f += (2 * n + 1) * Ff       # drift at every sigma point
+    f += 3 * tn                 # sigma points m ± sqrt(c) A_j
+    f += 3 * n * n              # d = fp - fm, fs += fp + fm
+    for j in range(n):          # G[:, j] = Ainv d
+        for i in range(n):
+            f += 1 + 2 * i
+    f += 3 * n                  # dm
+    if l_diag:
+        f += tn                 # Bq
+        for i in range(n):
+            for j in range(i + 1):
+                f += 1 + 2 * j
+    else:
+        for i in range(n):      # Z = Ainv Q
+            for j in range(n):
+                f += 2 * (i + 1)
+        for i in range(n):
+            for j in range(i + 1):
+                f += 2 * (j + 1)
+    f += 3 * tn + n             # g, kap*g + acc, halved diagonal
+    for i in range(n):          # dA = A Phi
+        for j in range(i + 1):
+            f += 1 + 2 * (i - j)
+    return f
+
+
+def step_flops(n: int, Ff: int, l_diag: bool = True) -> int:
+    ns = n + n * (n + 1) // 2
+    return 4 * rhs_flops(n, Ff, l_diag) + 4 * 4 * ns
+
+
+def update_flops(n: int, m: int, Fh: int) -> int:
+    s = 2 * n + 1
+    tn = n * (n + 1) // 2
+    f = s * Fh + 3 * tn                      # measurement images of the sigma points
+    f += m * (2 * n + 3)                     # mu
+    rows = s + m
+    per_row = 2 * m                          # deviation rows
+    for k in range(m):
+        per_row += 3 + 2 + 2 + 6 * (m - 1 - k)   # sqrt, recip, c, s, rotate the rest of the row
+    f += rows * per_row
+    for k in range(m):                       # column-0 up/down-date
+        f += 8 + 5 * (m - 1 - k)
+    f += m                                   # reciprocals of diag(srS)
+    for a in range(m):                       # w = srS^-1 r, dist, log
+        f += 1 + 2 * a + 1 + 2 + 1
+    for i in range(n):                       # C row and Z row
+        f += m * (3 * (i + 1) + 1)
+        for a in range(m):
+            f += 2 * a + 1
+    f += 2 * n * m                           # m += Z w
+    for _ in range(m):                       # m rank-1 downdates of A
+        for k in range(n):
+            f += 8 + 5 * (n - 1 - k)
+    return f + 4
+
+
+def kernel_flops(n, m, Ff, Fh, total_rk4_steps, timepoints, l_diag=True):
+    """Executed flops of one filter instance that takes ``total_rk4_steps`` RK4 steps over ``timepoints`` time points."""
+    return total_rk4_steps * step_flops(n, Ff, l_diag) + timepoints * update_flops(n, m, Fh)
+
+
+def survey_flops(n, m, Ff, Fh, total_rk4_steps, timepoints):
+    """F_rhs = s F_f + 7ns + 2n^2 s + 6n^2 + 3n^3, F_step = 4 F_rhs + 14ns, plus F_upd per time point."""
+    s = 2 * n + 1
+    o = m
+    rhs = s * Ff + 7 * n * s + 2 * n * n * s + 6 * n * n + 3 * n ** 3
+    step = 4 * rhs + 14 * n * s
+    upd = (s * Fh + 2 * m * s + 2 * (s + o) * o * o + 4 * o * o + (2 * n * o * s + 2 * n * s) + o ** 3 // 3 + 2 * n * o * o
+           + n * o * o + 3 * n * n * o + o * o + 2 * n * n)
+    return total_rk4_steps * step + timepoints * upd
+
+
+def rk4_step_count(t1: float, h: float) -> int:
+    """Steps odeint's integrate_const takes over [0, t1] with step h (rule T1): the remainder is dropped."""
+    eps = 2.220446049250313e-16
+    if not (h > 0) or t1 != t1:
+        return 0
+    step, time = 0, 0.0
+    while (time + h) - t1 <= eps:
+        step += 1
+        time = 0.0 + step * h
+    return step

@@ -378,17 +378,30 @@ def compileModel(psydiffModel, extra_flags: str = ""):
     if not ptr:
         raise PsydiffError(L.psy_last_error().decode())
     h = _Handle(ptr, cubin)
-    data = psydiffModel["data"]
-    obs_cm = np.asfortranarray(data["observations"], dtype=np.float64)
-    dt = np.ascontiguousarray(data["dt"], dtype=np.float64)
-    row_off = np.ascontiguousarray(psydiffModel["_row_off"], dtype=np.int64)
-    pid = np.ascontiguousarray(np.asarray(psydiffModel["_persons_unique"], dtype=np.float64).astype(np.int32))
-    _lib.check(L.psy_upload(ptr, obs_cm.shape[0], len(pid), obs_cm.ctypes.data_as(_lib.c_double_p), _lib.dptr(dt),
-                            _lib.i64ptr(row_off), _lib.iptr(pid)))
+    psydiffModel["_handle"] = h
+    uploadData(psydiffModel)
     ptab = psydiffModel["pars"]["parameterTable"]
     tidx = np.ascontiguousarray(ptab.theta_index, dtype=np.int32)
     _lib.check(L.psy_set_slots(ptr, len(ptab.theta_labels), _lib.iptr(tidx)))
-    psydiffModel["_handle"] = h
+    return psydiffModel
+
+
+def uploadData(psydiffModel):
+    """Copy model$data (host, R layout: observations rows x m column-major, dt, person blocks) into HBM.  compileModel
+    calls this once; call it again after replacing model["data"] with a dataset of the same persons (e.g. a new
+    simulation) — the slot map and the compiled kernel are kept."""
+    h = psydiffModel.get("_handle")
+    if h is None or not h.ptr:
+        raise PsydiffError("model is not compiled: call compileModel(model) first")
+    data = psydiffModel["data"]
+    obs_cm = data["observations"]
+    if not (isinstance(obs_cm, np.ndarray) and obs_cm.dtype == np.float64 and obs_cm.flags.f_contiguous):
+        obs_cm = np.asfortranarray(obs_cm, dtype=np.float64)
+    dt = np.ascontiguousarray(data["dt"], dtype=np.float64)
+    row_off = np.ascontiguousarray(psydiffModel["_row_off"], dtype=np.int64)
+    pid = np.ascontiguousarray(np.asarray(psydiffModel["_persons_unique"], dtype=np.float64).astype(np.int32))
+    _lib.check(_lib.lib().psy_upload(h.ptr, obs_cm.shape[0], len(pid), obs_cm.ctypes.data_as(_lib.c_double_p), _lib.dptr(dt),
+                                     _lib.i64ptr(row_off), _lib.iptr(pid)))
     return psydiffModel
 
 

@@ -90,12 +90,13 @@ def _vdp3_drift(x, mu, om, k):
     return dx
 
 
-def config_c4(N=1_000_000, T=100, seed=20210132, n_groups=8, **settings):
+def config_c4(N=1_000_000, T=100, seed=20210132, n_groups=8, id_offset=0, **settings):
     """C4: three diffusively coupled Van der Pol oscillators (n = m = 6, y = x), irregular time intervals,
     mu1..mu3 specific to 8 groups (P = 3*8 + 27 = 51 parameters, 30 per person -> 61 filter instances per person),
     fixed-step RK4 with the package default h = min(dt>0)/30."""
     rng = np.random.default_rng(seed)
-    group = (np.arange(N) % n_groups) + 1
+    ids = id_offset + np.arange(1, N + 1)          # person ids of this (shard of the) dataset
+    group = ((ids - 1) % n_groups) + 1
     mu_g = np.linspace(0.6, 1.4, n_groups)[:, None] * np.array([1.0, 0.9, 1.1])[None, :]   # [group, oscillator]
     om = np.array([1.0, 1.2, 0.8])
     kk = np.array([0.10, 0.05, 0.08, 0.12, 0.06, 0.09])
@@ -121,7 +122,7 @@ def config_c4(N=1_000_000, T=100, seed=20210132, n_groups=8, **settings):
                 k2 = _vdp3_drift(x + h[:, None] * k1, mu, om, kk)
                 x = x + 0.5 * h[:, None] * (k1 + k2) + ldiff * np.sqrt(h)[:, None] * rng.standard_normal((nb, 6))
             obs[c0:c1, t, :] = x + rsd * rng.standard_normal((nb, 6))
-    dataset = {"person": np.repeat(np.arange(1, N + 1), T), "observations": obs.reshape(N * T, 6), "dt": dts.reshape(-1)}
+    dataset = {"person": np.repeat(ids, T), "observations": obs.reshape(N * T, 6), "dt": dts.reshape(-1)}
     parameters = {"mu1": 1.0, "mu2": 0.9, "mu3": 1.1, "om1": 1.0, "om2": 1.2, "om3": 0.8,
                   "k12": 0.10, "k13": 0.05, "k21": 0.08, "k23": 0.12, "k31": 0.06, "k32": 0.09}
     Lm = np.full((6, 6), "0", dtype=object)
@@ -134,7 +135,7 @@ def config_c4(N=1_000_000, T=100, seed=20210132, n_groups=8, **settings):
         L=Lm, Rchol=Rm, A0=np.eye(6) * 0.5,
         m0=np.array([[f"m0_{i + 1} = {m0[i]}"] for i in range(6)], dtype=object),
         parameters=parameters,
-        grouping="mu1 | grp; mu2 | grp; mu3 | grp;", groupingvariables={"grp": group.astype(float)},
+        grouping="mu1 | grp; mu2 | grp; mu3 | grp;", groupingvariables={"grp": (((np.arange(1, id_offset + N + 1) - 1) % n_groups) + 1).astype(float)},  # indexed by id
         integrateFunction="rk4", eps=np.array([1e-6]), direction="central",
     )
     kw.update(settings)

@@ -1,0 +1,12 @@
+#!/bin/bash
+# one GPU round: parity tests, default bench, ncu launch list and one full capture of the filter kernel (small shard)
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 3000 gpurun_out/bench_default.json; tail -5 gpurun_out/bench_default.err
+CMD="python bench.py --persons-per-gpu 4096 --steps 1 --warmup 3 --no-cpu-baseline"
+$CMD > gpurun_out/plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+$CMD > gpurun_out/plain2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:psy_filter_kernel -s 3 -c 1 -o gpurun_out/prof $CMD > gpurun_out/ncu_full.log 2>&1
+tail -3 gpurun_out/ncu_full.log
+ls -la gpurun_out
