@@ -1,0 +1,214 @@
+"""Host logic and the C-ABI boundary without a GPU: symbol export, loud failure without a device, the model front end
+(newPsydiff parsing, log-Cholesky, grouping -> slot map), code generation + nvcc cross-compile, sweep bookkeeping,
+and the exported filter primitives."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import psydiff_b200 as pd
+from psydiff_b200 import _lib, codegen, synth
+from psydiff_b200._lib import PsydiffError
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    from psydiff_b200 import build
+    build.build_library()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "psydiff_b200.h")).read()
+    declared = set(re.findall(r"\b(psy_[A-Za-z0-9_]+)\s*\(", hdr))
+    assert len(declared) > 40
+    L = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/psydiff_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_compute_fails_loudly_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = _lib.lib()
+    model = pd.newPsydiff(**synth.config_c1(N=3, T=5))
+    with pytest.raises(PsydiffError, match="no CUDA device|CPU fallback"):
+        pd.compileModel(model)
+    with pytest.raises(PsydiffError, match="not compiled"):
+        pd.fitModel(model)
+    tf = C.c_double()
+    assert L.psy_measure_fp64_peak(C.byref(tf)) == 2   # PSY_ERR_CUDA
+
+
+def test_newpsydiff_parameter_table_and_logchol():
+    m = pd.newPsydiff(**synth.config_c1(N=4, T=6))
+    pt = m["pars"]["parameterTable"]
+    assert pt.theta_labels == ["drift_eta1", "drift_eta1_eta2", "drift_eta2_eta1", "drift_eta2", "mm_Y1", "mm_Y2",
+                               "lnT0var_eta1", "T0var_eta2_eta1", "lnT0var_eta2", "lneta1_eta1", "lneta2_eta2"]
+    v = pd.getParameterValues(m)
+    assert v["lneta1_eta1"] == pytest.approx(np.log(np.sqrt(.5)))     # chol2LogChol: log on the diagonal, "ln" prefix
+    assert v["lnT0var_eta1"] == 0.0 and v["T0var_eta2_eta1"] == 0.0
+    assert pt.theta_index.shape == (4, 11) and (pt.theta_index == np.arange(11)).all()
+    assert len(pt) == 44 and list(pt.label[:2]) == ["drift_eta1", "drift_eta1_eta2"]
+    assert m["timeStep"][0] == pytest.approx(1 / 30)
+    assert m["m2LL"].shape == (4,) and (m["latentScores"] == -99999.99).all()
+    # default timeStep (R/prepareModel.R:435-438)
+    kw = synth.config_c1(N=2, T=4)
+    kw.pop("timeStep")
+    assert np.allclose(pd.newPsydiff(**kw)["timeStep"], np.linspace(1 / 30, 1 / 10, 5))
+
+
+def test_grouping_person_and_group_labels():
+    kw = synth.config_c1(N=6, T=4)
+    kw["grouping"] = "mm_Y1 | person;\n mm_Y2 | group1;"
+    kw["groupingvariables"] = {"group1": np.array([1, 1, 1, 2, 2, 2])}
+    m = pd.newPsydiff(**kw)
+    pt = m["pars"]["parameterTable"]
+    labs = pt.theta_labels
+    assert "mm_Y1_p1" in labs and "mm_Y1_p6" in labs and "mm_Y2_p1" in labs and "mm_Y2_p2" in labs and "mm_Y1" not in labs
+    assert len(labs) == 9 + 6 + 2
+    # first-appearance order: person 1's rows first
+    assert labs[:6] == ["drift_eta1", "drift_eta1_eta2", "drift_eta2_eta1", "drift_eta2", "mm_Y1_p1", "mm_Y2_p1"]
+    k1, k2 = 4, 5
+    assert [labs[i] for i in pt.theta_index[:, k1]] == [f"mm_Y1_p{p}" for p in range(1, 7)]
+    assert [labs[i] for i in pt.theta_index[:, k2]] == ["mm_Y2_p1"] * 3 + ["mm_Y2_p2"] * 3
+    with pytest.raises(PsydiffError, match="not found in groupingvariables"):
+        pd.newPsydiff(**dict(kw, grouping="mm_Y1 | nope;"))
+
+
+def test_newpsydiff_errors_mirror_reference():
+    kw = synth.config_c1(N=2, T=4)
+    with pytest.raises(PsydiffError, match="to end with ;"):
+        pd.newPsydiff(**dict(kw, latentEquations="dx = DRIFT*x"))
+    with pytest.raises(PsydiffError, match="Unknown field in dataset"):
+        pd.newPsydiff(**dict(kw, dataset=dict(kw["dataset"], extra=1)))
+    with pytest.raises(PsydiffError, match="dataset must be a list"):
+        pd.newPsydiff(**dict(kw, dataset=[1, 2]))
+    with pytest.raises(PsydiffError, match="differ in their number of manifest"):
+        pd.newPsydiff(**dict(kw, Rchol=np.eye(3)))
+
+
+def test_set_get_parameter_values_and_changed_flags():
+    m = pd.newPsydiff(**synth.config_c1(N=3, T=4))
+    pt = m["pars"]["parameterTable"]
+    pt.changed[:] = False
+    pd.setParameterValues(pt, [0.25, -0.3], ["mm_Y1", "drift_eta1"])   # second value unchanged -> not flagged
+    assert pd.getParameterValues(m)["mm_Y1"] == 0.25
+    assert pt.changed[:, 4].all() and not pt.changed[:, 0].any()
+    with pytest.warns(UserWarning, match="not found in the parameterTable"):
+        pd.setParameterValues(pt, [1.0], ["nope"])
+    with pytest.raises(PsydiffError, match="does not match"):
+        pd.setParameterValues(pt, [1.0, 2.0], ["mm_Y1"])
+    c = pd.clonePsydiffModel(m)
+    pd.setParameterValues(c["pars"]["parameterTable"], {"mm_Y1": 9.0})
+    assert pd.getParameterValues(m)["mm_Y1"] == 0.25
+
+
+def test_codegen_and_cross_compile_for_sm100a():
+    m = pd.newPsydiff(**synth.config_c1(N=2, T=3))
+    src = m["cppCode"]
+    assert "psy_filter.cuh" in src and "dx = DRIFT*x;" in src and "PSY_INSTANTIATE" in src
+    assert "L_STRUCT = psy::L_DIAG" in src and "R_DIAG = true" in src
+    cubin = pd.compileModelSource(m)
+    assert os.path.getsize(cubin) > 10000
+    log = open(cubin.replace(".cubin", ".log")).read() if os.path.exists(cubin.replace(".cubin", ".log")) else ""
+    assert "sm_100a" in log or log == ""
+    # element-wise syntax variants of the reference examples (R/prepareModel.R:172-179, 345-355)
+    kw = synth.config_c1(N=2, T=3)
+    kw["parameters"] = {"a": -0.3, "b": 0.2, "lam": np.array([["1"], ["l2 = 0.5"]], dtype=object)}
+    kw["latentEquations"] = "dx(0) = a*x(0);\n dx[1] = b*x[0] - 0.5*x[1]*exp(-x(0)*x(0));"
+    kw["manifestEquations"] = "y(0) = x(0);\n y(1) = lam(1,0)*x(1) + sin(t)*0.0;"
+    assert os.path.exists(pd.compileModelSource(pd.newPsydiff(**kw)))
+
+
+def test_unsupported_equation_is_reported():
+    kw = synth.config_c1(N=2, T=3)
+    kw["latentEquations"] = "arma::mat E = arma::expmat(DRIFT); dx = E*x;"
+    with pytest.raises(PsydiffError, match="unsupported on device"):
+        pd.compileModelSource(pd.newPsydiff(**kw))
+    with pytest.raises(ValueError, match="lower triangular"):
+        pd.newPsydiff(**dict(synth.config_c1(N=2, T=3), A0=np.array([[1.0, 0.3], [0.0, 1.0]])))
+
+
+def _sweep(P, levels, direction=0):
+    """levels: list of (eps, partial vector).  Returns grad, total."""
+    L = _lib.lib()
+    s = L.psy_sweep_create(P)
+    need = np.zeros(2 * P + 1, dtype=np.uint8)
+    done = C.c_int(0)
+    for lv, (eps, part) in enumerate(levels):
+        part = np.ascontiguousarray(part, dtype=np.float64)
+        _lib.check(L.psy_sweep_resolve(s, _lib.dptr(part), eps, lv, len(levels), direction, _lib.u8ptr(need), C.byref(done)))
+        if done.value:
+            break
+    g = np.zeros(P)
+    tot = C.c_double()
+    _lib.check(L.psy_sweep_finish(s, direction, _lib.dptr(g), C.byref(tot)))
+    L.psy_sweep_destroy(s)
+    return g, tot.value, need
+
+
+def test_sweep_bookkeeping_eps_fallback():
+    P = 3
+
+    def part(total, nb, Dp, Dm, nfp, nfm, nbt):
+        return np.concatenate([[total, nb], Dp, Dm, nfp, nfm, nbt])
+    # level 0: parameter 1's left side fails (one non-finite person); level 1 repairs it with a larger eps
+    l0 = part(100.0, 0, [1e-6, 2e-6, 3e-6], [-1e-6, np.nan, -3e-6], [0, 0, 0], [0, 1, 0], [0, 0, 0])
+    l1 = part(100.0, 0, [0, 0, 0], [0, -2e-5, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0])
+    g, tot, _ = _sweep(P, [(1e-8, l0), (1e-6, l1)])
+    assert tot == 100.0
+    assert g[0] == pytest.approx(2e-6 / 2e-8) and g[2] == pytest.approx(6e-6 / 2e-8)
+    assert g[1] == pytest.approx((2e-6 + 2e-5) / (1e-8 + 1e-6))       # denominators: eps actually used on each side
+    # exhausted eps[] -> NaN entry, others unaffected
+    g, _, _ = _sweep(P, [(1e-8, l0)])
+    assert np.isnan(g[1]) and np.isfinite(g[[0, 2]]).all()
+    # a non-finite base person outside the touched set poisons every total -> all NaN
+    lb = part(np.nan, 1, [1e-6] * 3, [-1e-6] * 3, [0] * 3, [0] * 3, [0] * 3)
+    assert np.isnan(_sweep(P, [(1e-8, lb)])[0]).all()
+    # one-sided directions
+    gl, _, _ = _sweep(P, [(1e-6, l1)], direction=1)
+    assert gl[1] == pytest.approx(2e-5 / 1e-6)
+    with pytest.raises(PsydiffError, match="Unknown direction"):
+        _sweep(P, [(1e-6, l1)], direction=7)
+
+
+def test_exported_primitives_match_oracle_primitives():
+    from oracle.oracle import _lib as orc
+    O, L = orc(), _lib.lib()
+    rng = np.random.default_rng(1)
+    n, m = 3, 2
+    s = 2 * n + 1
+    wm, wc, wm2 = np.zeros(s), np.zeros(s), np.zeros(s)
+    L.psy_getMeanWeights(n, .2, 2., 0., _lib.dptr(wm)); L.psy_getCovWeights(n, .2, 2., 0., _lib.dptr(wc))
+    O.psy_oracle_getMeanWeights(C.c_int(n), C.c_double(.2), C.c_double(2.), C.c_double(0.), _lib.dptr(wm2))
+    assert np.allclose(wm, wm2) and abs(wm.sum() - 1) < 1e-12
+    Y = np.asfortranarray(rng.standard_normal((m, s)))
+    mu = np.zeros(m)
+    L.psy_predictMu(m, s, _lib.dptr(Y), _lib.dptr(wm), _lib.dptr(mu))
+    assert np.allclose(mu, Y @ wm)
+    Rc = np.asfortranarray(np.diag([.5, .7]))
+    a, b = np.zeros((m, m), order="F"), np.zeros((m, m), order="F")
+    L.psy_predictSquareRootOfS(m, s, _lib.dptr(Y), _lib.dptr(mu), _lib.dptr(Rc), wc[0], wc[1], _lib.dptr(a))
+    O.psy_oracle_predictSquareRootOfS(C.c_int(m), C.c_int(s), _lib.dptr(Y), _lib.dptr(mu), _lib.dptr(Rc), C.c_double(wc[0]), C.c_double(wc[1]), _lib.dptr(b))
+    assert np.allclose(a, b, atol=1e-12)
+    # computeIndividualM2LL (R/RcppExports.R:214) against the closed form
+    S = a @ a.T
+    raw = rng.standard_normal(m)
+    out = C.c_double()
+    L.psy_computeIndividualM2LL(m, _lib.dptr(raw), _lib.dptr(mu), _lib.dptr(np.asfortranarray(S)), C.byref(out))
+    r = raw - mu
+    assert out.value == pytest.approx(m * np.log(2 * np.pi) + np.linalg.slogdet(S)[1] + r @ np.linalg.solve(S, r))
+    out2 = C.c_double()
+    L.psy_computeIndividualM2LLChol(m, _lib.dptr(raw), _lib.dptr(mu), _lib.dptr(a), C.byref(out2))
+    assert out2.value == pytest.approx(out.value)
+    assert L.psy_cholupdate(m, _lib.dptr(a), _lib.dptr(raw), 1.0, b"sideways") == 1     # Rcpp::stop on unknown direction
+    X = np.asfortranarray(rng.standard_normal((7, 3)))
+    R = np.zeros((3, 3), order="F")
+    L.psy_qr(7, 3, _lib.dptr(X), _lib.dptr(R))
+    assert np.allclose(R.T @ R, X.T @ X)
