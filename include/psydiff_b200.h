@@ -42,6 +42,9 @@ typedef struct psy_model psy_model;
 /* thread-local message of the last failing call on this thread */
 const char* psy_last_error(void);
 int psy_version(void);
+/* steps Boost.odeint's integrate_const(runge_kutta4, sys, x, 0, t1, h) takes (R/modelTemplate.R:327-329): the count the
+ * kernel uses per observation interval; the remainder of the interval is not integrated. */
+int psy_rk4_step_count(double t1, double h);
 
 /* ---- compileModel (R/prepareModel.R:553-562) ---------------------------------------------------------------
  * The reference writes model$cppCode to a temp file and hands it to Rcpp::sourceCpp (host g++).  Here the
@@ -55,6 +58,10 @@ int psy_model_compile(const char* cuda_source, const char* include_dir, const ch
  * per-person parameterTable, R/prepareModel.R:467-472), and load the compiled module onto the current device. */
 psy_model* psy_model_create(int n, int m, int nfree, const char* cubin_path);
 void psy_model_destroy(psy_model* mdl);
+/* Replace the handle's kernel module (same n, m, slots) keeping the resident dataset and slot map — used when
+ * model$integrateFunction or srUpdate change after compileModel: the stepper and the update variant are compile-time
+ * properties of the generated kernel. */
+int psy_model_load_module(psy_model* mdl, const char* cubin_path);
 
 /* Settings that fitModel reads back from the model list on every call (R/modelTemplate.R:169-176):
  * alpha, beta, kappa, timeStep[], integrateFunction; sr = srUpdate of newPsydiff (R/prepareModel.R:403). */

@@ -30,9 +30,11 @@ c_ubyte_p = C.POINTER(C.c_ubyte)
 SIGNATURES = {
     "psy_last_error": (C.c_char_p, []),
     "psy_version": (C.c_int, []),
+    "psy_rk4_step_count": (C.c_int, [C.c_double, C.c_double]),
     "psy_model_compile": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
     "psy_model_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_char_p]),
     "psy_model_destroy": (None, [C.c_void_p]),
+    "psy_model_load_module": (C.c_int, [C.c_void_p, C.c_char_p]),
     "psy_model_settings": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, c_double_p, C.c_int, C.c_int]),
     "psy_upload": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, c_double_p, c_double_p, c_int64_p, c_int_p]),
     "psy_set_slots": (C.c_int, [C.c_void_p, C.c_int, c_int_p]),

@@ -52,6 +52,7 @@ struct Drv {
   CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
   CUresult (*ModuleUnload)(CUmodule) = nullptr;
   CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*) = nullptr;
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
   CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
@@ -68,7 +69,7 @@ int load_driver() {
   CU_TRY(cudaFree(0));
   struct { const char* name; void** slot; } tab[] = {
       {"cuModuleLoadData", (void**)&g_drv.ModuleLoadData}, {"cuModuleUnload", (void**)&g_drv.ModuleUnload},
-      {"cuModuleGetFunction", (void**)&g_drv.ModuleGetFunction}, {"cuLaunchKernel", (void**)&g_drv.LaunchKernel},
+      {"cuModuleGetFunction", (void**)&g_drv.ModuleGetFunction}, {"cuModuleGetGlobal", (void**)&g_drv.ModuleGetGlobal}, {"cuLaunchKernel", (void**)&g_drv.LaunchKernel},
       {"cuFuncGetAttribute", (void**)&g_drv.FuncGetAttribute}, {"cuGetErrorString", (void**)&g_drv.GetErrorString}};
   for (auto& t : tab) {
     cudaDriverEntryPointQueryResult qr;
@@ -136,6 +137,7 @@ struct psy_model {
   CUmodule mod = nullptr;
   CUfunction fn = nullptr;
   int block = 128;  // = the module's __launch_bounds__ block size
+  int mod_stepper = 0, mod_sr = 1;  // what the loaded module was generated for (psy_module_info)
   // host copies
   std::vector<double> h_dt;
   std::vector<int64_t> h_row_off;
@@ -262,30 +264,30 @@ std::string slurp(const std::string& path) {
 
 bool file_exists(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 && st.st_size > 0; }
 
-// odeint integrate_const step count, rule T1: exact IEEE, evaluated on the host once per distinct dt
+// odeint integrate_const step count, rule T1: steps are taken for k = 0, 1, ... while
+//   ((0 + k*h) + h) - t1 <= DBL_EPSILON      (exact IEEE double, no FMA; this file's host code is compiled without contraction)
+// and the remainder interval is dropped.  The predicate is monotone in k, so the count is found from the guess
+// floor(t1/h) by local search instead of walking all k — same integer, O(1) per row.
+inline bool t1_cond(int k, double h, double t1) {
+  volatile double time = 0.0 + (double)k * h;
+  volatile double next = time + h;
+  return (next - t1) <= DBL_EPSILON;
+}
 int rk4_step_count(double t1, double h) {
-  if (!(h > 0) || !(t1 == t1)) return 0;
-  int step = 0;
-  double time = 0.0;
-  while ((time + h) - t1 <= DBL_EPSILON) {
-    ++step;
-    time = 0.0 + (double)step * h;
-    if (step > 50000000) break;
-  }
-  return step;
+  if (!(h > 0) || !(t1 == t1) || !(t1 > 0)) return 0;
+  double q = std::floor(t1 / h);
+  if (q > 5e7) q = 5e7;
+  int k = (int)q;
+  while (k > 0 && !t1_cond(k - 1, h, t1)) --k;
+  while (k < 50000000 && t1_cond(k, h, t1)) ++k;
+  return k;
 }
 
 int ensure_ksteps(psy_model* M) {
   const double h = M->time_step.empty() ? 0.0 : M->time_step[0];
   if (M->ksteps_h == h && M->d_ksteps.p) return PSY_OK;
   std::vector<int> ks(M->rows);
-  std::unordered_map<double, int> cache;
-  for (int64_t r = 0; r < M->rows; r++) {
-    const double d = M->h_dt[r];
-    auto it = cache.find(d);
-    if (it == cache.end()) it = cache.emplace(d, rk4_step_count(d, h)).first;
-    ks[r] = it->second;
-  }
+  for (int64_t r = 0; r < M->rows; r++) ks[r] = rk4_step_count(M->h_dt[r], h);
   int rc = M->d_ksteps.upload(ks.data(), ks.size());
   if (rc) return rc;
   M->ksteps_h = h;
@@ -298,6 +300,10 @@ int launch_filter(psy_model* M, const PsyInst* d_list, const int* d_out_idx, int
   if (!M->d_obs.p) return fail(PSY_ERR_STATE, "psy_upload has not been called");
   if (!M->d_tidx.p) return fail(PSY_ERR_STATE, "psy_set_slots has not been called");
   if (M->time_step.empty()) return fail(PSY_ERR_STATE, "psy_model_settings has not been called");
+  const int want_stepper = (M->stepper == PSY_STEPPER_DOPRI5) ? 1 : 0;  // "default" == rk4 (a NaN state stays NaN under dopri5)
+  if (want_stepper != M->mod_stepper || (M->sr ? 1 : 0) != M->mod_sr)
+    return fail(PSY_ERR_STATE, "loaded module was generated for stepper=%d srUpdate=%d but the settings ask for stepper=%d srUpdate=%d: "
+                "recompile the model (psy_model_compile + psy_model_load_module)", M->mod_stepper, M->mod_sr, want_stepper, M->sr ? 1 : 0);
   if (count <= 0) return PSY_OK;
   if (count > 2147483000LL) return fail(PSY_ERR_ARG, "too many instances for one launch (%lld)", (long long)count);
   int rc = ensure_ksteps(M);
@@ -355,6 +361,7 @@ extern "C" {
 
 const char* psy_last_error(void) { return g_err.c_str(); }
 int psy_version(void) { return 100; }
+int psy_rk4_step_count(double t1, double h) { return rk4_step_count(t1, h); }
 
 int psy_model_compile(const char* cuda_source, const char* include_dir, const char* cache_dir, const char* extra_flags,
                       char* cubin_path, size_t cap) {
@@ -398,19 +405,42 @@ int psy_model_compile(const char* cuda_source, const char* include_dir, const ch
   return PSY_OK;
 }
 
+int psy_model_load_module(psy_model* M, const char* cubin_path) {
+  if (!M || !cubin_path) return fail(PSY_ERR_ARG, "psy_model_load_module: bad arguments");
+  int rc = load_driver();
+  if (rc) return rc;
+  std::string image = slurp(cubin_path);
+  if (image.empty()) return fail(PSY_ERR_ARG, "cannot read compiled module %s", cubin_path);
+  CUmodule mod = nullptr;
+  CUfunction fn = nullptr;
+  CUresult r = g_drv.ModuleLoadData(&mod, image.data());
+  if (r != CUDA_SUCCESS) return fail(PSY_ERR_CUDA, "cuModuleLoadData(%s): %s", cubin_path, cu_str(r));
+  r = g_drv.ModuleGetFunction(&fn, mod, "psy_filter_kernel");
+  if (r != CUDA_SUCCESS) { g_drv.ModuleUnload(mod); return fail(PSY_ERR_CUDA, "psy_filter_kernel not found in %s: %s", cubin_path, cu_str(r)); }
+  int info[5] = {0, 1, M->n, M->m, M->F};
+  CUdeviceptr gp = 0;
+  size_t gs = 0;
+  if (g_drv.ModuleGetGlobal(&gp, &gs, mod, "psy_module_info") == CUDA_SUCCESS && gs == sizeof info)
+    CU_TRY(cudaMemcpy(info, (const void*)gp, sizeof info, cudaMemcpyDeviceToHost));
+  if (info[2] != M->n || info[3] != M->m || info[4] != M->F) {
+    g_drv.ModuleUnload(mod);
+    return fail(PSY_ERR_ARG, "module %s was generated for n=%d m=%d slots=%d, handle has n=%d m=%d slots=%d", cubin_path, info[2],
+                info[3], info[4], M->n, M->m, M->F);
+  }
+  if (M->mod) g_drv.ModuleUnload(M->mod);
+  M->mod = mod; M->fn = fn; M->mod_stepper = info[0]; M->mod_sr = info[1];
+  int mt = 0;
+  M->block = 128;
+  if (g_drv.FuncGetAttribute(&mt, CU_FUNC_ATTRIBUTE_MAX_THREADS_PER_BLOCK, M->fn) == CUDA_SUCCESS && mt >= 32 && mt <= 256) M->block = mt;
+  return PSY_OK;
+}
+
 psy_model* psy_model_create(int n, int m, int nfree, const char* cubin_path) {
   if (n < 1 || m < 1 || nfree < 0 || !cubin_path) { fail(PSY_ERR_ARG, "psy_model_create: bad arguments"); return nullptr; }
   if (load_driver()) return nullptr;
-  std::string image = slurp(cubin_path);
-  if (image.empty()) { fail(PSY_ERR_ARG, "cannot read compiled module %s", cubin_path); return nullptr; }
   psy_model* M = new psy_model;
   M->n = n; M->m = m; M->F = nfree;
-  CUresult r = g_drv.ModuleLoadData(&M->mod, image.data());
-  if (r != CUDA_SUCCESS) { fail(PSY_ERR_CUDA, "cuModuleLoadData(%s): %s", cubin_path, cu_str(r)); delete M; return nullptr; }
-  r = g_drv.ModuleGetFunction(&M->fn, M->mod, "psy_filter_kernel");
-  if (r != CUDA_SUCCESS) { fail(PSY_ERR_CUDA, "psy_filter_kernel not found in %s: %s", cubin_path, cu_str(r)); g_drv.ModuleUnload(M->mod); delete M; return nullptr; }
-  int mt = 0;
-  if (g_drv.FuncGetAttribute(&mt, CU_FUNC_ATTRIBUTE_MAX_THREADS_PER_BLOCK, M->fn) == CUDA_SUCCESS && mt >= 32 && mt <= 256) M->block = mt;
+  if (psy_model_load_module(M, cubin_path)) { delete M; return nullptr; }
   cudaEventCreate(&M->ev0);
   cudaEventCreate(&M->ev1);
   return M;
@@ -553,7 +583,6 @@ int psy_set_slots(psy_model* M, int P, const int* tidx) {
 int psy_fit(psy_model* M, const double* theta, int skip_update, double* m2ll, double* latent_cm, double* pred_cm) {
   if (!M || !m2ll || (M->P > 0 && !theta)) return fail(PSY_ERR_ARG, "psy_fit: bad arguments");
   if (!M->d_tidx.p) return fail(PSY_ERR_STATE, "psy_fit: call psy_upload and psy_set_slots first");
-  if (!M->sr) return fail(PSY_ERR_STATE, "this module was loaded for srUpdate=TRUE only");
   int rc;
   if (M->P > 0) CU_TRY(cudaMemcpy(M->d_theta.p, theta, sizeof(double) * M->P, cudaMemcpyHostToDevice));
   double *dl = nullptr, *dp = nullptr;
@@ -584,7 +613,6 @@ int psy_grad_level(psy_model* M, const double* theta, double eps, int direction,
   if (!M || (M->P > 0 && !theta)) return fail(PSY_ERR_ARG, "psy_grad_level: bad arguments");
   if (direction < 0 || direction > 2) return fail(PSY_ERR_ARG, "Unknown direction argument. Possible are central, left and right");
   if (!M->d_tidx.p) return fail(PSY_ERR_STATE, "psy_grad_level: call psy_upload and psy_set_slots first");
-  if (!M->sr) return fail(PSY_ERR_STATE, "this module was loaded for srUpdate=TRUE only");
   int rc;
   if (M->P > 0) CU_TRY(cudaMemcpy(M->d_theta.p, theta, sizeof(double) * M->P, cudaMemcpyHostToDevice));
   const bool all = (direction == PSY_DIR_CENTRAL) && !need;

@@ -200,59 +200,190 @@ struct Filter {
     }
   }
 
-  // ---- measurement update, SR variant (R/modelTemplate.R:352-408).  Returns this time point's -2LL term. -----
-  static __device__ __forceinline__ double update_sr(const double (&p)[F], double (&m)[N], double (&A)[TN],
-                                                     const double (&ob)[M], const UT& ut, int person, double tabs,
-                                                     bool skip_update, double* pred_row) {
-    // sigma points of (m, A) and their images (getY_, R/modelTemplate.R:62-73); t is ABSOLUTE time here
-    Vec<M> Y0, Yp[N], Ym[N];
-    {
-      Vec<N> xc;
+  // ---- adaptive Dormand-Prince 5(4) (Boost.odeint integrate() = integrate_adaptive(controlled_runge_kutta<
+  // runge_kutta_dopri5>, eps_abs = eps_rel = 1e-6, a_x = a_dxdt = 1), call sites R/modelTemplate.R:331-333; rule T2 of
+  // SURVEY §8c).  The controller's error norm is the max over the entries of the FULL sigma-point matrix, so it is
+  // evaluated on the implied columns m, m ± sqrt(c) A_j of the reduced state.  A fresh stepper per observation interval
+  // (FSAL derivative recomputed at t = 0).  On step-size underflow (odeint throws) or a NaN error the state is NaN.
+  static constexpr int NS = N + TN;
+  static __device__ __forceinline__ void rhs_z(const double (&p)[F], const double (&z)[NS], double (&k)[NS],
+                                               const double (&Q)[QLEN], const UT& ut, int person, double t) {
+    rhs(p, reinterpret_cast<const double(&)[N]>(z[0]), reinterpret_cast<const double(&)[TN]>(z[N]),
+        reinterpret_cast<double(&)[N]>(k[0]), reinterpret_cast<double(&)[TN]>(k[N]), Q, ut, person, t);
+  }
+  static __device__ __forceinline__ double err_entry(double xe, double x, double dx, double dt) {
+    return fabs(xe) / (1e-6 + 1e-6 * (fabs(x) + fabs(dt) * fabs(dx)));
+  }
+  static __device__ void dopri5(const double (&p)[F], double (&m)[N], double (&A)[TN], const double (&Q)[QLEN],
+                                             const UT& ut, int person, double t1, double dt) {
+    constexpr double a21 = 1.0 / 5, a31 = 3.0 / 40, a32 = 9.0 / 40, a41 = 44.0 / 45, a42 = -56.0 / 15, a43 = 32.0 / 9,
+                     a51 = 19372.0 / 6561, a52 = -25360.0 / 2187, a53 = 64448.0 / 6561, a54 = -212.0 / 729,
+                     a61 = 9017.0 / 3168, a62 = -355.0 / 33, a63 = 46732.0 / 5247, a64 = 49.0 / 176, a65 = -5103.0 / 18656,
+                     c1 = 35.0 / 384, c3 = 500.0 / 1113, c4 = 125.0 / 192, c5 = -2187.0 / 6784, c6 = 11.0 / 84;
+    constexpr double e1 = c1 - 5179.0 / 57600, e3 = c3 - 7571.0 / 16695, e4 = c4 - 393.0 / 640,
+                     e5 = c5 + 92097.0 / 339200, e6 = c6 - 187.0 / 2100, e7 = -1.0 / 40;
+    constexpr double DEPS = 2.220446049250313e-16;
+    double z[NS], k1[NS], k2[NS], k3[NS], k4[NS], k5[NS], k6[NS], k7[NS], zt[NS], zn[NS];
 #pragma unroll
-      for (int i = 0; i < N; i++) xc.v[i] = m[i];
-      Y0.zeros();
-      Mdl::measurementEquation(xc, Y0, p, person, tabs);
+    for (int i = 0; i < N; i++) z[i] = m[i];
 #pragma unroll
-      for (int j = 0; j < N; j++) {
-        Vec<N> xp, xm;
+    for (int i = 0; i < TN; i++) z[N + i] = A[i];
+    double t = 0.0;
+    bool dead = false;
+    rhs_z(p, z, k1, Q, ut, person, t);
+#pragma unroll 1
+    while (t1 - t > DEPS && !dead) {
+      if ((t + dt) - t1 > DEPS) dt = t1 - t;
+      int tries = 0;
+#pragma unroll 1
+      for (;;) {
+        if (++tries > 500) { dead = true; break; }
+#pragma unroll
+        for (int i = 0; i < NS; i++) zt[i] = z[i] + dt * (a21 * k1[i]);
+        rhs_z(p, zt, k2, Q, ut, person, t + dt * (1.0 / 5));
+#pragma unroll
+        for (int i = 0; i < NS; i++) zt[i] = z[i] + dt * (a31 * k1[i] + a32 * k2[i]);
+        rhs_z(p, zt, k3, Q, ut, person, t + dt * (3.0 / 10));
+#pragma unroll
+        for (int i = 0; i < NS; i++) zt[i] = z[i] + dt * (a41 * k1[i] + a42 * k2[i] + a43 * k3[i]);
+        rhs_z(p, zt, k4, Q, ut, person, t + dt * (4.0 / 5));
+#pragma unroll
+        for (int i = 0; i < NS; i++) zt[i] = z[i] + dt * (a51 * k1[i] + a52 * k2[i] + a53 * k3[i] + a54 * k4[i]);
+        rhs_z(p, zt, k5, Q, ut, person, t + dt * (8.0 / 9));
+#pragma unroll
+        for (int i = 0; i < NS; i++) zt[i] = z[i] + dt * (a61 * k1[i] + a62 * k2[i] + a63 * k3[i] + a64 * k4[i] + a65 * k5[i]);
+        rhs_z(p, zt, k6, Q, ut, person, t + dt);
+#pragma unroll
+        for (int i = 0; i < NS; i++) zn[i] = z[i] + dt * (c1 * k1[i] + c3 * k3[i] + c4 * k4[i] + c5 * k5[i] + c6 * k6[i]);
+        rhs_z(p, zn, k7, Q, ut, person, t + dt);
+        // error estimate, entry by entry over the implied sigma-point matrix (old state and old derivative)
+        double xe[NS];
+#pragma unroll
+        for (int i = 0; i < NS; i++) xe[i] = dt * (e1 * k1[i] + e3 * k3[i] + e4 * k4[i] + e5 * k5[i] + e6 * k6[i] + e7 * k7[i]);
+        double err = 0.0;
+        bool bad = false;
 #pragma unroll
         for (int i = 0; i < N; i++) {
-          if (i >= j) {
-            double d = ut.sqrtc * A[tri(i, j)];
-            xp.v[i] = m[i] + d;
-            xm.v[i] = m[i] - d;
-          } else {
-            xp.v[i] = m[i];
-            xm.v[i] = m[i];
+          const double e = err_entry(xe[i], z[i], k1[i], dt);
+          bad = bad || (e != e);
+          err = fmax(err, e);
+#pragma unroll
+          for (int j = 0; j <= i; j++) {
+            const int q = N + tri(i, j);
+            const double ep = err_entry(xe[i] + ut.sqrtc * xe[q], z[i] + ut.sqrtc * z[q], k1[i] + ut.sqrtc * k1[q], dt);
+            const double em = err_entry(xe[i] - ut.sqrtc * xe[q], z[i] - ut.sqrtc * z[q], k1[i] - ut.sqrtc * k1[q], dt);
+            bad = bad || (ep != ep) || (em != em);
+            err = fmax(err, fmax(ep, em));
           }
         }
-        Yp[j].zeros();
-        Ym[j].zeros();
-        Mdl::measurementEquation(xp, Yp[j], p, person, tabs);
-        Mdl::measurementEquation(xm, Ym[j], p, person, tabs);
+        if (bad) { dead = true; break; }
+        if (err > 1.0) {
+          dt *= fmax(0.9 * pow(err, -1.0 / 3.0), 0.2);
+          continue;
+        }
+        t += dt;
+        if (err < 0.5) dt *= 0.9 * pow(fmax(3.2e-4, err), -1.0 / 5.0);  // 5^-5 = 3.2e-4
+#pragma unroll
+        for (int i = 0; i < NS; i++) { z[i] = zn[i]; k1[i] = k7[i]; }
+        break;
       }
     }
+    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+    for (int i = 0; i < N; i++) m[i] = dead ? nanv : z[i];
+#pragma unroll
+    for (int i = 0; i < TN; i++) A[i] = dead ? nanv : z[N + i];
+  }
+
+  // ---- predicted manifests: images of the sigma points of (m, A) (getY_, R/modelTemplate.R:62-73, 353-358) --------
+  struct Meas {
+    Vec<M> Y0, Yp[N], Ym[N];
     double mu[M];
+    bool miss[M];
+    int o;
+  };
+  static __device__ __forceinline__ void predict_meas(const double (&p)[F], const double (&m)[N], const double (&A)[TN],
+                                                      const double (&ob)[M], const UT& ut, int person, double tabs, Meas& z) {
+    Vec<N> xc;
+#pragma unroll
+    for (int i = 0; i < N; i++) xc.v[i] = m[i];
+    z.Y0.zeros();
+    Mdl::measurementEquation(xc, z.Y0, p, person, tabs);  // t is ABSOLUTE time here (timeSum)
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      Vec<N> xp, xm;
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        if (i >= j) {
+          xp.v[i] = fma(ut.sqrtc, A[tri(i, j)], m[i]);
+          xm.v[i] = fma(-ut.sqrtc, A[tri(i, j)], m[i]);
+        } else {
+          xp.v[i] = m[i];
+          xm.v[i] = m[i];
+        }
+      }
+      z.Yp[j].zeros();
+      z.Ym[j].zeros();
+      Mdl::measurementEquation(xp, z.Yp[j], p, person, tabs);
+      Mdl::measurementEquation(xm, z.Ym[j], p, person, tabs);
+    }
 #pragma unroll
     for (int a = 0; a < M; a++) {
       double acc = 0.0;
 #pragma unroll
-      for (int j = 0; j < N; j++) acc += Yp[j].v[a] + Ym[j].v[a];
-      mu[a] = ut.wm0 * Y0.v[a] + ut.wm1 * acc;  // predictMu_C
+      for (int j = 0; j < N; j++) acc += z.Yp[j].v[a] + z.Ym[j].v[a];
+      z.mu[a] = ut.wm0 * z.Y0.v[a] + ut.wm1 * acc;  // predictMu_C
     }
-    if (pred_row) {
-#pragma unroll
-      for (int a = 0; a < M; a++) pred_row[a] = mu[a];
-    }
-    bool miss[M];
-    int o = 0;
+    z.o = 0;
 #pragma unroll
     for (int a = 0; a < M; a++) {
-      miss[a] = !isfinite(ob[a]);
-      o += miss[a] ? 0 : 1;
+      z.miss[a] = !isfinite(ob[a]);
+      z.o += z.miss[a] ? 0 : 1;
     }
-    if (o == 0 || skip_update) return 0.0;
+  }
 
+  // Z = C srS^-T with C = X W Y' = wc1 sqrt(c) Σ_j A_j (Yp_j − Ym_j)' (predictC_C; the column-0 term is (x_0 − X wm) = 0),
+  // w = srS^-1 (obs − mu); returns dist = w'w and Σ log diag(srS) over the observed manifests.
+  // K = Z srS^-1 (computeK_SR_C / computeK_C) is never formed:  K (obs − mu) = Z w,  K srS = Z,  K S K' = Z Z'.
+  static __device__ __forceinline__ void gain(const double (&A)[TN], const Meas& z, const double (&ob)[M], const double (&S)[TM],
+                                              const UT& ut, double (&Z)[N][M], double (&w)[M], double& dist, double& ld) {
+    double rS[M];
+#pragma unroll
+    for (int a = 0; a < M; a++) rS[a] = 1.0 / S[tri(a, a)];
+    dist = 0.0;
+    ld = 0.0;
+#pragma unroll
+    for (int a = 0; a < M; a++) {
+      double acc = z.miss[a] ? 0.0 : (ob[a] - z.mu[a]);
+#pragma unroll
+      for (int k = 0; k < a; k++) acc -= S[tri(a, k)] * w[k];
+      w[a] = acc * rS[a];
+      dist += w[a] * w[a];
+      ld += z.miss[a] ? 0.0 : log(S[tri(a, a)]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      double crow[M];
+#pragma unroll
+      for (int a = 0; a < M; a++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j <= i; j++) acc += A[tri(i, j)] * (z.Yp[j].v[a] - z.Ym[j].v[a]);
+        crow[a] = z.miss[a] ? 0.0 : ut.kap * acc;
+      }
+#pragma unroll
+      for (int a = 0; a < M; a++) {
+        double acc = crow[a];
+#pragma unroll
+        for (int k = 0; k < a; k++) acc -= Z[i][k] * S[tri(a, k)];
+        Z[i][a] = acc * rS[a];
+      }
+    }
+  }
+
+  // ---- measurement update, SR variant (R/modelTemplate.R:363-408).  Returns this time point's -2LL term. ---------
+  static __device__ __forceinline__ double update_sr(const double (&p)[F], double (&m)[N], double (&A)[TN],
+                                                     const double (&ob)[M], const UT& ut, const Meas& z) {
     // srS = chol factor of wc1 Σ_i (Y_i − mu)(·)ᵀ + Rchol Rcholᵀ  (predictSquareRootOfS_C: QR of [√wc1 (Y−mu), Rchol]ᵀ).
     // The QR is done as a streaming Givens triangularisation, one row of the stacked matrix at a time; its R
     // factor has a positive diagonal, which is the sign convention cholupdate_C normalises to anyway (T3).
@@ -283,18 +414,18 @@ struct Filter {
     {
       double tr[M];
 #pragma unroll
-      for (int a = 0; a < M; a++) tr[a] = miss[a] ? 0.0 : sw * (Y0.v[a] - mu[a]);
+      for (int a = 0; a < M; a++) tr[a] = z.miss[a] ? 0.0 : sw * (z.Y0.v[a] - z.mu[a]);
       rotate_in(tr);
 #pragma unroll
       for (int j = 0; j < N; j++) {
 #pragma unroll
-        for (int a = 0; a < M; a++) tr[a] = miss[a] ? 0.0 : sw * (Yp[j].v[a] - mu[a]);
+        for (int a = 0; a < M; a++) tr[a] = z.miss[a] ? 0.0 : sw * (z.Yp[j].v[a] - z.mu[a]);
         rotate_in(tr);
       }
 #pragma unroll
       for (int j = 0; j < N; j++) {
 #pragma unroll
-        for (int a = 0; a < M; a++) tr[a] = miss[a] ? 0.0 : sw * (Ym[j].v[a] - mu[a]);
+        for (int a = 0; a < M; a++) tr[a] = z.miss[a] ? 0.0 : sw * (z.Ym[j].v[a] - z.mu[a]);
         rotate_in(tr);
       }
       // columns of Rchol = logChol2Chol(RLogChol) (R/modelTemplate.R:277-278), masked
@@ -305,10 +436,10 @@ struct Filter {
         if constexpr (Mdl::R_DIAG) {
 #pragma unroll
           for (int a = 0; a < M; a++) tr[a] = 0.0;
-          tr[b] = miss[b] ? 1.0 : Rc[b + b * M];
+          tr[b] = z.miss[b] ? 1.0 : Rc[b + b * M];
         } else {
 #pragma unroll
-          for (int a = 0; a < M; a++) tr[a] = (miss[a] || miss[b]) ? ((a == b) ? 1.0 : 0.0) : Rc[a + b * M];
+          for (int a = 0; a < M; a++) tr[a] = (z.miss[a] || z.miss[b]) ? ((a == b) ? 1.0 : 0.0) : Rc[a + b * M];
         }
         rotate_in(tr);
       }
@@ -320,7 +451,7 @@ struct Filter {
       const double v4 = sqrt(sqrt(fabs(ut.wc0)));
       double x[M];
 #pragma unroll
-      for (int a = 0; a < M; a++) x[a] = miss[a] ? 0.0 : v4 * (Y0.v[a] - mu[a]);
+      for (int a = 0; a < M; a++) x[a] = z.miss[a] ? 0.0 : v4 * (z.Y0.v[a] - z.mu[a]);
 #pragma unroll
       for (int k = 0; k < M; k++) {
         const double lkk = S[tri(k, k)];
@@ -337,41 +468,8 @@ struct Filter {
         }
       }
     }
-    double rS[M];
-#pragma unroll
-    for (int a = 0; a < M; a++) rS[a] = 1.0 / S[tri(a, a)];
-    // w = srS⁻¹ (obs − mu): gives both the Mahalanobis term and, through Z, the mean update
-    double w[M], dist = 0.0, ld = 0.0;
-#pragma unroll
-    for (int a = 0; a < M; a++) {
-      double acc = miss[a] ? 0.0 : (ob[a] - mu[a]);
-#pragma unroll
-      for (int k = 0; k < a; k++) acc -= S[tri(a, k)] * w[k];
-      w[a] = acc * rS[a];
-      dist += w[a] * w[a];
-      ld += miss[a] ? 0.0 : log(S[tri(a, a)]);
-    }
-    // C = X W Yᵀ = wc1 sqrt(c) Σ_j A_j (Yp_j − Ym_j)ᵀ (predictC_C; the column-0 term is (x_0 − X wm) = 0).
-    // Z = C srS⁻ᵀ.  K = Z srS⁻¹ (computeK_SR_C) is never formed:  K (obs − mu) = Z w  and  U = K srS = Z.
-    double Z[N][M];
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-      double crow[M];
-#pragma unroll
-      for (int a = 0; a < M; a++) {
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j <= i; j++) acc += A[tri(i, j)] * (Yp[j].v[a] - Ym[j].v[a]);
-        crow[a] = miss[a] ? 0.0 : ut.kap * acc;
-      }
-#pragma unroll
-      for (int a = 0; a < M; a++) {
-        double acc = crow[a];
-#pragma unroll
-        for (int k = 0; k < a; k++) acc -= Z[i][k] * S[tri(a, k)];
-        Z[i][a] = acc * rS[a];
-      }
-    }
+    double Z[N][M], w[M], dist, ld;
+    gain(A, z, ob, S, ut, Z, w, dist, ld);
 #pragma unroll
     for (int i = 0; i < N; i++) {
       double acc = 0.0;
@@ -379,10 +477,10 @@ struct Filter {
       for (int a = 0; a < M; a++) acc += Z[i][a] * w[a];
       m[i] += acc;  // updateM_C
     }
-    // A ← cholupdate(A, U[:,b], 1, "downdate") for every manifest b (R/modelTemplate.R:382-386)
+    // A ← cholupdate(A, U[:,b], 1, "downdate") for every manifest b (R/modelTemplate.R:382-386), U = K srS = Z
 #pragma unroll
     for (int b = 0; b < M; b++) {
-      if (miss[b]) continue;  // U[:,b] is exactly zero: the downdate would be an exact no-op
+      if (z.miss[b]) continue;  // U[:,b] is exactly zero: the downdate would be an exact no-op
       double x[N];
 #pragma unroll
       for (int i = 0; i < N; i++) x[i] = Z[i][b];
@@ -403,7 +501,62 @@ struct Filter {
       }
     }
     // computeIndividualM2LLChol_C (inst/include/psydiffInternals.h:117-131)
-    return (double)o * 1.8378770664093453 + 2.0 * ld + dist;
+    return (double)z.o * 1.8378770664093453 + 2.0 * ld + dist;
+  }
+
+  // ---- measurement update, covariance variant (srUpdate = FALSE, R/modelTemplate.R:785-835) -----------------------
+  // S = Y W Y' + R with the textbook weights (predictS_C, Internals.h:81-83), symmetric by construction; its Cholesky
+  // factor gives K = C S^-1 (computeK_C), log det S and the Mahalanobis term (computeIndividualM2LL_C, :103-115);
+  // P = P_ − K S K' = P_ − Z Z' (updateP_C).  RR = Rchol Rchol' (full product, then the observed sub-block).
+  static __device__ __forceinline__ double update_cov(double (&m)[N], const double (&A)[TN], double (&P)[TN],
+                                                      const double (&RR)[TM], const double (&ob)[M], const UT& ut, const Meas& z) {
+    double S[TM];
+#pragma unroll
+    for (int a = 0; a < M; a++)
+#pragma unroll
+      for (int b = 0; b <= a; b++) {
+        double acc = ut.wc0 * (z.Y0.v[a] - z.mu[a]) * (z.Y0.v[b] - z.mu[b]);
+        double s2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; j++)
+          s2 += (z.Yp[j].v[a] - z.mu[a]) * (z.Yp[j].v[b] - z.mu[b]) + (z.Ym[j].v[a] - z.mu[a]) * (z.Ym[j].v[b] - z.mu[b]);
+        acc += ut.wc1 * s2 + RR[tri(a, b)];
+        S[tri(a, b)] = (z.miss[a] || z.miss[b]) ? ((a == b) ? 1.0 : 0.0) : acc;
+      }
+    // in-place Cholesky of S
+#pragma unroll
+    for (int j = 0; j < M; j++) {
+      double d = S[tri(j, j)];
+#pragma unroll
+      for (int k = 0; k < j; k++) d -= S[tri(j, k)] * S[tri(j, k)];
+      d = sqrt(d);
+      S[tri(j, j)] = d;
+      const double id = 1.0 / d;
+#pragma unroll
+      for (int i = j + 1; i < M; i++) {
+        double a = S[tri(i, j)];
+#pragma unroll
+        for (int k = 0; k < j; k++) a -= S[tri(i, k)] * S[tri(j, k)];
+        S[tri(i, j)] = a * id;
+      }
+    }
+    double Z[N][M], w[M], dist, ld;
+    gain(A, z, ob, S, ut, Z, w, dist, ld);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      double acc = 0.0;
+#pragma unroll
+      for (int a = 0; a < M; a++) acc += Z[i][a] * w[a];
+      m[i] += acc;
+#pragma unroll
+      for (int j = 0; j <= i; j++) {
+        double zz = 0.0;
+#pragma unroll
+        for (int a = 0; a < M; a++) zz += Z[i][a] * Z[j][a];
+        P[tri(i, j)] -= zz;
+      }
+    }
+    return (double)z.o * 1.8378770664093453 + 2.0 * ld + dist;
   }
 
   // ---- one instance through all of its person's time points ------------------------------------------------
@@ -462,18 +615,83 @@ struct Filter {
     const long long r0 = __ldg(L.row_off + person);
     const int T = (int)(__ldg(L.row_off + person + 1) - r0);
     const bool base = (in.code < 0);
+    // covariance variant state: P = A0 A0', R = Rchol Rchol' (R/modelTemplate.R:694-698)
+    double P[Mdl::SR ? 1 : TN], RR[Mdl::SR ? 1 : TM];
+    if constexpr (!Mdl::SR) {
+#pragma unroll
+      for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k <= j; k++) acc += A[tri(i, k)] * A[tri(j, k)];
+          P[tri(i, j)] = acc;
+        }
+      double Rc[M * M];
+      Mdl::rchol(Rc, p);
+#pragma unroll
+      for (int a = 0; a < M; a++)
+#pragma unroll
+        for (int b = 0; b <= a; b++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < M; k++) acc += Rc[a + k * M] * Rc[b + k * M];
+          RR[tri(a, b)] = acc;
+        }
+    }
     double f = 0.0, tabs = 0.0;
 #pragma unroll 1
     for (int tp = 0; tp < T; tp++) {
       const long long row = r0 + tp;
       const double dtv = __ldg(L.dt + row);
       tabs += dtv;
-      if (dtv != 0.0) rk4(p, m, A, Q, ut, pid, L.h, __ldg(L.ksteps + row));
+      if constexpr (!Mdl::SR) {
+        // A = chol(P_, "lower") at every time point (R/modelTemplate.R:720); a non-positive pivot gives NaN
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+          double d = P[tri(j, j)];
+#pragma unroll
+          for (int k = 0; k < j; k++) d -= A[tri(j, k)] * A[tri(j, k)];
+          d = sqrt(d);
+          A[tri(j, j)] = d;
+          const double id = 1.0 / d;
+#pragma unroll
+          for (int i = j + 1; i < N; i++) {
+            double a = P[tri(i, j)];
+#pragma unroll
+            for (int k = 0; k < j; k++) a -= A[tri(i, k)] * A[tri(j, k)];
+            A[tri(i, j)] = a * id;
+          }
+        }
+      }
+      if (dtv != 0.0) {
+        if constexpr (Mdl::STEPPER == 1) dopri5(p, m, A, Q, ut, pid, dtv, L.h);
+        else rk4(p, m, A, Q, ut, pid, L.h, __ldg(L.ksteps + row));
+        if constexpr (!Mdl::SR) {  // P_ = computePFromSigmaPoints_C (R/modelTemplate.R:771)
+#pragma unroll
+          for (int i = 0; i < N; i++)
+#pragma unroll
+            for (int j = 0; j <= i; j++) {
+              double acc = 0.0;
+#pragma unroll
+              for (int k = 0; k <= j; k++) acc += A[tri(i, k)] * A[tri(j, k)];
+              P[tri(i, j)] = acc;
+            }
+        }
+      }
       double ob[M];
 #pragma unroll
       for (int a = 0; a < M; a++) ob[a] = __ldg(L.obs + row * M + a);
-      double* prow = (base && L.pred) ? (L.pred + row * M) : nullptr;
-      f += update_sr(p, m, A, ob, ut, pid, tabs, L.skip_update != 0, prow);
+      Meas ms;
+      predict_meas(p, m, A, ob, ut, pid, tabs, ms);
+      if (base && L.pred) {
+#pragma unroll
+        for (int a = 0; a < M; a++) L.pred[row * M + a] = ms.mu[a];  // R/modelTemplate.R:361
+      }
+      if (ms.o > 0 && !L.skip_update) {
+        if constexpr (Mdl::SR) f += update_sr(p, m, A, ob, ut, ms);
+        else f += update_cov(m, A, P, RR, ob, ut, ms);
+      }
       if (base && L.latent) {
 #pragma unroll
         for (int i = 0; i < N; i++) L.latent[row * N + i] = m[i];
@@ -485,7 +703,9 @@ struct Filter {
 
 }  // namespace psy
 
-#define PSY_INSTANTIATE(MODEL)                                                                  \
-  extern "C" __global__ void __launch_bounds__(PSY_BLOCK, PSY_MIN_BLOCKS) psy_filter_kernel(const PsyLaunch L) { \
-    psy::Filter<MODEL>::run(L);                                                                 \
+// psy_module_info = {stepper, srUpdate, nlatent, nmanifest, free slots}: lets the host check a module against its settings
+#define PSY_INSTANTIATE(MODEL)                                                                                      \
+  extern "C" __device__ const int psy_module_info[5] = {MODEL::STEPPER, MODEL::SR ? 1 : 0, MODEL::N, MODEL::M, MODEL::NSLOT}; \
+  extern "C" __global__ void __launch_bounds__(PSY_BLOCK, PSY_MIN_BLOCKS) psy_filter_kernel(const PsyLaunch L) {   \
+    psy::Filter<MODEL>::run(L);                                                                                     \
   }

@@ -19,6 +19,7 @@ from . import _lib, codegen
 from ._lib import PsydiffError
 
 _PERSON_WORDS = ("person", "persons", "individual", "individuals")  # R/prepareModel.R:717
+_STEPPERS = {"rk4": 0, "runge_kutta_dopri5": 1}
 
 
 def _rnum(v) -> str:
@@ -321,7 +322,8 @@ def newPsydiff(dataset, latentEquations, manifestEquations, L, Rchol, A0, m0, gr
     ptab = ParameterTable(slot_rows, persons_unique, theta_labels, theta_values, theta_index)
 
     spec = codegen.ModelSpec(nlatent=nlatent, nmanifest=nmanifest, containers=containers, n_slots=len(slot_rows),
-                             latentEquations=latentEquations, manifestEquations=manifestEquations, srUpdate=bool(srUpdate))
+                             latentEquations=latentEquations, manifestEquations=manifestEquations, srUpdate=bool(srUpdate),
+                             stepper=_STEPPERS.get(integrateFunction, 0))
     cuda_src = codegen.emit_cuda(spec)
 
     model = PsydiffModel(
@@ -359,9 +361,25 @@ class _Handle:
             pass
 
 
+def _variant(model):
+    """(stepper, srUpdate) the kernel must be generated for; "default" integrates with rk4 (R/modelTemplate.R:334-344:
+    dopri5 is only tried on an already non-finite state, which stays non-finite)."""
+    return (1 if model["integrateFunction"] == "runge_kutta_dopri5" else 0, bool(model.get("srUpdate", True)))
+
+
+def _sync_source(model):
+    """Regenerate model["cppCode"] if integrateFunction / srUpdate were changed after newPsydiff."""
+    spec = model["_spec"]
+    st, sr = _variant(model)
+    if (spec.stepper, spec.srUpdate) != (st, sr):
+        spec.stepper, spec.srUpdate = st, sr
+        model["cppCode"] = codegen.emit_cuda(spec)
+
+
 def compileModelSource(psydiffModel, extra_flags: str = "") -> str:
     """Compile the model's CUDA TU to a cubin for sm_100a (no GPU needed).  Returns the cubin path."""
     L = _lib.lib()
+    _sync_source(psydiffModel)
     buf = C.create_string_buffer(4096)
     _lib.check(L.psy_model_compile(psydiffModel["cppCode"].encode(), _lib.CSRC_DIR.encode(), _lib.CACHE_DIR.encode(),
                                    extra_flags.encode(), buf, 4096))
@@ -378,6 +396,8 @@ def compileModel(psydiffModel, extra_flags: str = ""):
     if not ptr:
         raise PsydiffError(L.psy_last_error().decode())
     h = _Handle(ptr, cubin)
+    h.variant = _variant(psydiffModel)
+    h.extra_flags = extra_flags
     psydiffModel["_handle"] = h
     uploadData(psydiffModel)
     ptab = psydiffModel["pars"]["parameterTable"]
@@ -405,13 +425,16 @@ def uploadData(psydiffModel):
     return psydiffModel
 
 
-_STEPPERS = {"rk4": 0, "runge_kutta_dopri5": 1}
-
-
 def _push_settings(model):
     h = model.get("_handle")
     if h is None or not h.ptr:
         raise PsydiffError("model is not compiled: call compileModel(model) first")
+    if getattr(h, "variant", None) != _variant(model):
+        # the reference reads integrateFunction at every fitModel call (R/modelTemplate.R:174); here the stepper and the
+        # update variant are baked into the kernel, so a change swaps in the matching module (cached after the first time)
+        cubin = compileModelSource(model, getattr(h, "extra_flags", ""))
+        _lib.check(_lib.lib().psy_model_load_module(h.ptr, cubin.encode()))
+        h.variant, h.cubin = _variant(model), cubin
     ts = np.ascontiguousarray(model["timeStep"], dtype=np.float64)
     stepper = _STEPPERS.get(model["integrateFunction"], 2)  # anything else is the "default" branch (R/modelTemplate.R:334)
     _lib.check(_lib.lib().psy_model_settings(h.ptr, float(model["alpha"]), float(model["beta"]), float(model["kappa"]),

@@ -140,3 +140,40 @@ def config_c4(N=1_000_000, T=100, seed=20210132, n_groups=8, id_offset=0, **sett
     )
     kw.update(settings)
     return kw
+
+
+def config_c3(N=250_000, T=100, seed=20210131, id_offset=0, **settings):
+    """C3: Van der Pol oscillator dx0 = x1; dx1 = mu_p (1 − x0²) x1 − om² x0 with a person-specific mu ("mu | person;",
+    mu_p ~ U(0.5, 1.5)), common om, L = diag(.1), Rchol = diag(.3), dt = 0.25, adaptive Dormand–Prince
+    (integrateFunction = "runge_kutta_dopri5", initial step dt/30).  P = N + 7 parameters, 8 per person -> 17 instances."""
+    rng = np.random.default_rng(seed)
+    ids = id_offset + np.arange(1, N + 1)
+    mu = rng.uniform(0.5, 1.5, size=N)
+    om, ldiff, rsd, dt = 1.0, 0.1, 0.3, 0.25
+    x = np.array([1.0, 0.0])[None, :] + 0.3 * rng.standard_normal((N, 2))
+    obs = np.empty((N, T, 2))
+    nsub, h = 5, dt / 5
+
+    def f(x):
+        return np.stack([x[:, 1], mu * (1.0 - x[:, 0] ** 2) * x[:, 1] - om * om * x[:, 0]], axis=1)
+    for t in range(T):
+        if t > 0:
+            for _ in range(nsub):
+                k1 = f(x)
+                k2 = f(x + h * k1)
+                x = x + 0.5 * h * (k1 + k2) + ldiff * np.sqrt(h) * rng.standard_normal((N, 2))
+        obs[:, t, :] = x + rsd * rng.standard_normal((N, 2))
+    dts = np.tile(np.concatenate([[0.0], np.full(T - 1, dt)]), N)
+    dataset = {"person": np.repeat(ids, T), "observations": obs.reshape(N * T, 2), "dt": dts}
+    kw = dict(
+        dataset=dataset,
+        latentEquations="dx(0) = x(1);\ndx(1) = mu*(1.0 - x(0)*x(0))*x(1) - om*om*x(0);",
+        manifestEquations="y(0) = x(0);\ny(1) = x(1);",
+        L=np.array([["l1 = 0.1", "0"], ["0", "l2 = 0.1"]], dtype=object),
+        Rchol=np.array([["r1 = 0.3", "0"], ["0", "r2 = 0.3"]], dtype=object),
+        A0=np.eye(2) * 0.3, m0=np.array([["m0_1 = 1.0"], ["m0_2 = 0.0"]], dtype=object),
+        parameters={"mu": 1.0, "om": 1.0}, grouping="mu | person;",
+        timeStep=np.array([dt / 30]), integrateFunction="runge_kutta_dopri5", eps=np.array([1e-6]), direction="central",
+    )
+    kw.update(settings)
+    return kw

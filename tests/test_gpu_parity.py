@@ -138,3 +138,101 @@ def test_eps_fallback_and_nan_pattern():
     g = pd.getGradients(model)
     gref = _oracle(model).gradients()
     assert np.array_equal(np.isfinite(list(g.values())), np.isfinite(gref["grad_clean"]))
+
+
+def test_covariance_variant_srUpdate_false():
+    # a24: fitModel covariance variant (R/modelTemplate.R:583-847)
+    model = pd.newPsydiff(**synth.config_c1(N=24, T=30, missing=0.2, seed=9, srUpdate=False))
+    _check_fit(model)
+    _check_grad(model)
+    m4 = pd.newPsydiff(**synth.config_c4(N=8, T=10, srUpdate=False))
+    fit, ref = _check_fit(m4)
+    assert np.isfinite(fit["m2LL"]).all()
+
+
+def test_dopri5_linear_and_c3():
+    # a10: integrate() = controlled dopri5 (R/modelTemplate.R:331-333)
+    model = pd.newPsydiff(**synth.config_c1(N=16, T=20, integrateFunction="runge_kutta_dopri5"))
+    _check_fit(model)
+    c3 = pd.newPsydiff(**synth.config_c3(N=64, T=24))
+    pt = c3["pars"]["parameterTable"]
+    assert len(pt.theta_labels) == 64 + 7 and "mu_p1" in pt.theta_labels and "mu_p64" in pt.theta_labels
+    fit, ref = _check_fit(c3)
+    assert np.isfinite(fit["m2LL"]).all()
+    _check_grad(c3, extended=True)
+
+
+def test_stepper_switch_after_compile_swaps_module():
+    # the reference reads integrateFunction at every fitModel call (R/modelTemplate.R:174)
+    model = pd.newPsydiff(**synth.config_c1(N=8, T=12))
+    pd.compileModel(model)
+    a = pd.fitModel(model)["m2LL"].copy()
+    model["integrateFunction"] = "runge_kutta_dopri5"
+    b = pd.fitModel(model)["m2LL"].copy()
+    assert not np.array_equal(a, b) and np.allclose(a, b, rtol=1e-5)
+    ref = _oracle(model).fit()["m2LL"]
+    assert np.max(np.abs(b - ref) / np.abs(ref)) < M2LL_RTOL
+    model["integrateFunction"] = "default"                  # rk4 (+ dopri5 only on a non-finite state)
+    assert np.array_equal(pd.fitModel(model)["m2LL"], a)
+
+
+def test_get_gradient_single_parameter_and_parallel_alias():
+    model = pd.newPsydiff(**synth.config_c1(N=6, T=10))
+    pd.compileParallelGradients(model, nCores=2)
+    assert model["cl"] is not None
+    g = pd.getGradientsParallel(model)
+    vals = pd.getParameterValues(model)
+    for par in (0, 5, 10):
+        one = pd.getGradient(model, vals, par)
+        (lab, v), = one.items()
+        assert lab == list(g.keys())[par] and v == g[lab]
+    pd.stopParallelGradients(model)
+
+
+def test_golden_fixtures():
+    import json, os
+    here = os.path.dirname(os.path.abspath(__file__))
+    g1 = json.load(open(os.path.join(here, "golden", "c1_oracle.json")))
+    m = pd.newPsydiff(**synth.config_c1())
+    pd.compileModel(m)
+    f = pd.fitModel(m)
+    assert np.max(np.abs(f["m2LL"] - np.array(g1["m2LL"])) / np.abs(g1["m2LL"])) < M2LL_RTOL
+    assert np.max(np.abs(f["m2LL"] - np.array(g1["exact_kf_m2LL"])) / np.abs(g1["m2LL"])) < 1e-9   # exact Kalman filter
+    assert np.allclose(f["latentScores"][:50], np.array(g1["latentScores_first_person"]), atol=1e-9)
+    gv = np.array(list(pd.getGradients(m).values()))
+    assert np.allclose(gv, g1["grad_clean"], rtol=1e-6, atol=1e-5)
+    g4 = json.load(open(os.path.join(here, "golden", "c4_oracle_ext.json")))
+    m4 = pd.newPsydiff(**synth.config_c4(N=16, T=12))
+    pd.compileModel(m4)
+    f4 = pd.fitModel(m4)["m2LL"]
+    assert np.max(np.abs(f4 - np.array(g4["m2LL"])) / np.abs(g4["m2LL"])) < 1e-10
+    gv4 = np.array(list(pd.getGradients(m4).values()))
+    assert np.max(np.abs(gv4 - np.array(g4["grad_clean"])) / np.abs(g4["grad_clean"])) < GRAD_RTOL
+
+
+def test_full_size_c2_properties():
+    """C2 at BASELINE.json's size (N = 100k, T = 100, 5 % missing): size-independent properties + an oracle subsample."""
+    N, T = 100_000, 100
+    kw = synth.config_c2(N=N, T=T)
+    obs = kw["dataset"]["observations"]
+    obs[(N - 1) * T:] = obs[:T]              # the last person is a copy of the first one
+    model = pd.newPsydiff(**kw)
+    pd.compileModel(model)
+    f = pd.fitModel(model)["m2LL"]
+    assert np.isfinite(f).all() and f[0] == f[N - 1]          # identical persons -> bit-identical -2LL
+    g = pd.getGradients(model)
+    # oracle on a 64-person subsample of the same model
+    sub = np.arange(0, N, N // 64)[:64]
+    ref = _oracle(model).fit(persons=sub, states=False)["m2LL"]
+    assert np.max(np.abs(f[sub] - ref) / np.abs(ref)) < M2LL_RTOL
+    # linearity over person shards: Σ-2LL and the gradient of the halves add up to the whole
+    halves = []
+    for lo, hi in ((0, N // 2), (N // 2, N)):
+        k2 = dict(kw)
+        k2["dataset"] = {k: v[lo * T:hi * T] for k, v in kw["dataset"].items()}
+        mh = pd.newPsydiff(**k2)
+        pd.compileModel(mh)
+        halves.append((pd.fitModel(mh)["m2LL"], np.array(list(pd.getGradients(mh).values()))))
+    assert np.array_equal(np.concatenate([halves[0][0], halves[1][0]]), f)
+    gv = np.array(list(g.values()))
+    assert np.allclose(halves[0][1] + halves[1][1], gv, rtol=1e-7, atol=1e-6 * np.abs(gv).max())
