@@ -55,6 +55,7 @@ struct Drv {
   CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*) = nullptr;
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
   CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
   bool ok = false;
 };
@@ -70,7 +71,7 @@ int load_driver() {
   struct { const char* name; void** slot; } tab[] = {
       {"cuModuleLoadData", (void**)&g_drv.ModuleLoadData}, {"cuModuleUnload", (void**)&g_drv.ModuleUnload},
       {"cuModuleGetFunction", (void**)&g_drv.ModuleGetFunction}, {"cuModuleGetGlobal", (void**)&g_drv.ModuleGetGlobal}, {"cuLaunchKernel", (void**)&g_drv.LaunchKernel},
-      {"cuFuncGetAttribute", (void**)&g_drv.FuncGetAttribute}, {"cuGetErrorString", (void**)&g_drv.GetErrorString}};
+      {"cuFuncGetAttribute", (void**)&g_drv.FuncGetAttribute}, {"cuFuncSetAttribute", (void**)&g_drv.FuncSetAttribute}, {"cuGetErrorString", (void**)&g_drv.GetErrorString}};
   for (auto& t : tab) {
     cudaDriverEntryPointQueryResult qr;
     cudaError_t ee = cudaGetDriverEntryPoint(t.name, t.slot, cudaEnableDefault, &qr);
@@ -137,12 +138,14 @@ struct psy_model {
   CUmodule mod = nullptr;
   CUfunction fn = nullptr;
   int block = 128;  // = the module's __launch_bounds__ block size
+  int smem_bytes = 0;  // dynamic shared memory the kernel asks for (psy_module_info[5])
   int mod_stepper = 0, mod_sr = 1;  // what the loaded module was generated for (psy_module_info)
   // host copies
   std::vector<double> h_dt;
   std::vector<int64_t> h_row_off;
   std::vector<int> h_tidx;           // N x F
-  std::vector<int64_t> h_inst_off;   // N+1
+  std::vector<int64_t> h_inst_off;   // N+1 (end of each person's possibly padded block)
+  std::vector<int64_t> h_inst_start; // N first instance (= base instance) of each person
   std::vector<int> h_dl;             // distinct theta lists, flattened at (inst_off[p]-p... ) see set_slots
   std::vector<int64_t> h_dl_off;     // N+1
   std::vector<int64_t> h_seg_off;    // P+1 (pairs per theta)
@@ -154,7 +157,7 @@ struct psy_model {
   DevBuf<long long> d_row_off;
   DevBuf<PsyInst> d_inst, d_inst_sub, d_inst_base;
   DevBuf<Chunk> d_chunks;
-  int64_t n_inst = 0, n_chunks = 0;
+  int64_t n_inst = 0, n_inst_real = 0, n_chunks = 0;  // n_inst counts padding slots, n_inst_real does not
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0.0;
   int64_t last_instances = 0;
@@ -329,7 +332,7 @@ int launch_filter(psy_model* M, const PsyInst* d_list, const int* d_out_idx, int
   const unsigned grid = (unsigned)((count + block - 1) / block);
   void* args[] = {&L};
   CU_TRY(cudaEventRecord(M->ev0, 0));
-  CUresult r = g_drv.LaunchKernel(M->fn, grid, 1, 1, block, 1, 1, 0, (CUstream)0, args, nullptr);
+  CUresult r = g_drv.LaunchKernel(M->fn, grid, 1, 1, block, 1, 1, (unsigned)M->smem_bytes, (CUstream)0, args, nullptr);
   if (r != CUDA_SUCCESS) return fail(PSY_ERR_CUDA, "cuLaunchKernel(psy_filter_kernel): %s", cu_str(r));
   CU_TRY(cudaEventRecord(M->ev1, 0));
   g_launches++;
@@ -417,7 +420,7 @@ int psy_model_load_module(psy_model* M, const char* cubin_path) {
   if (r != CUDA_SUCCESS) return fail(PSY_ERR_CUDA, "cuModuleLoadData(%s): %s", cubin_path, cu_str(r));
   r = g_drv.ModuleGetFunction(&fn, mod, "psy_filter_kernel");
   if (r != CUDA_SUCCESS) { g_drv.ModuleUnload(mod); return fail(PSY_ERR_CUDA, "psy_filter_kernel not found in %s: %s", cubin_path, cu_str(r)); }
-  int info[5] = {0, 1, M->n, M->m, M->F};
+  int info[6] = {0, 1, M->n, M->m, M->F, 0};
   CUdeviceptr gp = 0;
   size_t gs = 0;
   if (g_drv.ModuleGetGlobal(&gp, &gs, mod, "psy_module_info") == CUDA_SUCCESS && gs == sizeof info)
@@ -428,7 +431,11 @@ int psy_model_load_module(psy_model* M, const char* cubin_path) {
                 info[3], info[4], M->n, M->m, M->F);
   }
   if (M->mod) g_drv.ModuleUnload(M->mod);
-  M->mod = mod; M->fn = fn; M->mod_stepper = info[0]; M->mod_sr = info[1];
+  M->mod = mod; M->fn = fn; M->mod_stepper = info[0]; M->mod_sr = info[1]; M->smem_bytes = info[5];
+  if (M->smem_bytes > 48 * 1024) {
+    r = g_drv.FuncSetAttribute(M->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, M->smem_bytes);
+    if (r != CUDA_SUCCESS) return fail(PSY_ERR_CUDA, "cannot reserve %d bytes of shared memory: %s", M->smem_bytes, cu_str(r));
+  }
   int mt = 0;
   M->block = 128;
   if (g_drv.FuncGetAttribute(&mt, CU_FUNC_ATTRIBUTE_MAX_THREADS_PER_BLOCK, M->fn) == CUDA_SUCCESS && mt >= 32 && mt <= 256) M->block = mt;
@@ -516,7 +523,8 @@ int psy_set_slots(psy_model* M, int P, const int* tidx) {
   M->P = P;
   M->h_tidx.assign(tidx, tidx + (size_t)N * F);
   // distinct theta per person, in slot order
-  M->h_dl.clear(); M->h_dl_off.assign(N + 1, 0); M->h_inst_off.assign(N + 1, 0);
+  M->h_dl.clear(); M->h_dl_off.assign(N + 1, 0); M->h_inst_off.assign(N + 1, 0); M->h_inst_start.assign(N, 0);
+  int64_t n_real = 0;
   std::vector<int64_t> cnt(P + 1, 0);
   for (int p = 0; p < N; p++) {
     const int* row = tidx + (size_t)p * F;
@@ -527,18 +535,28 @@ int psy_set_slots(psy_model* M, int P, const int* tidx) {
       if (!seen) { M->h_dl.push_back(row[k]); cnt[row[k]]++; }
     }
     M->h_dl_off[p + 1] = (int64_t)M->h_dl.size();
-    M->h_inst_off[p + 1] = M->h_inst_off[p] + 1 + 2 * (int64_t)(M->h_dl.size() - b);
+    // Warp alignment: lanes of one warp then share their person's dt sequence and missingness pattern, so the RK4 step
+    // loop does not diverge.  A person's block is padded to a multiple of 32 only when that idles < 10 % of its lanes.
+    const int64_t cnt_p = 1 + 2 * (int64_t)(M->h_dl.size() - b);
+    const int64_t padded = (cnt_p + 31) / 32 * 32;
+    int64_t start = M->h_inst_off[p];
+    const bool align = (padded - cnt_p) * 10 <= cnt_p;
+    if (align) start = (start + 31) / 32 * 32;
+    M->h_inst_start[p] = start;
+    M->h_inst_off[p + 1] = start + (align ? padded : cnt_p);
+    n_real += cnt_p;
   }
   M->n_inst = M->h_inst_off[N];
+  M->n_inst_real = n_real;
   if (M->n_inst > 2147483000LL) return fail(PSY_ERR_ARG, "instance count %lld exceeds the per-rank limit; shard persons over more ranks", (long long)M->n_inst);
-  std::vector<PsyInst> inst((size_t)M->n_inst), base((size_t)N);
+  std::vector<PsyInst> inst((size_t)M->n_inst, PsyInst{-1, -1}), base((size_t)N);
   M->h_seg_off.assign(P + 1, 0);
   for (int t = 0; t < P; t++) M->h_seg_off[t + 1] = M->h_seg_off[t] + cnt[t];
   const int64_t n_pairs = M->h_seg_off[P];
   std::vector<int> pair_minus((size_t)n_pairs + N), pair_base((size_t)n_pairs + N);
   std::vector<int64_t> fill(M->h_seg_off.begin(), M->h_seg_off.end() - 1);
   for (int p = 0; p < N; p++) {
-    int64_t o = M->h_inst_off[p];
+    int64_t o = M->h_inst_start[p];
     inst[o] = PsyInst{p, -1};
     base[p] = PsyInst{p, -1};
     int64_t j = 0;
@@ -607,7 +625,7 @@ int psy_fit(psy_model* M, const double* theta, int skip_update, double* m2ll, do
 }
 
 int64_t psy_partial_len(const psy_model* M) { return M ? 5 * (int64_t)M->P + 2 : 0; }
-int64_t psy_n_instances(const psy_model* M) { return M ? M->n_inst : 0; }
+int64_t psy_n_instances(const psy_model* M) { return M ? M->n_inst_real : 0; }
 
 int psy_grad_level(psy_model* M, const double* theta, double eps, int direction, const unsigned char* need, void** partial_device) {
   if (!M || (M->P > 0 && !theta)) return fail(PSY_ERR_ARG, "psy_grad_level: bad arguments");
@@ -624,7 +642,7 @@ int psy_grad_level(psy_model* M, const double* theta, double eps, int direction,
     std::vector<int> oidx;
     const bool with_base = !need;  // the first level of a one-sided sweep also needs f0
     for (int p = 0; p < M->N; p++) {
-      const int64_t o = M->h_inst_off[p];
+      const int64_t o = M->h_inst_start[p];
       if (with_base) { sub.push_back(PsyInst{p, -1}); oidx.push_back((int)o); }
       int64_t j = 0;
       for (int64_t q = M->h_dl_off[p]; q < M->h_dl_off[p + 1]; q++, j++) {

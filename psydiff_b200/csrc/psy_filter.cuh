@@ -44,6 +44,23 @@ __host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j
 
 enum { L_DIAG = 0, L_FULL = 1 };
 
+// Reciprocal without the IEEE-division slow path: hardware seed (rcp.approx.ftz.f64, >= 20 mantissa bits) + two
+// Newton steps -> error <= ~1 ulp, no branches.  0 -> inf -> NaN downstream, like the reference's 1/0.
+// (-DPSY_IEEE_DIV restores 1.0 / x.)
+__device__ __forceinline__ double rcp(double x) {
+#ifdef PSY_IEEE_DIV
+  return 1.0 / x;
+#else
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+#endif
+}
+
 template <class Mdl>
 struct Filter {
   static constexpr int N = Mdl::N, M = Mdl::M, F = Mdl::NFREE;  // NFREE >= 1 (padded); NSLOT real slots
@@ -59,7 +76,7 @@ struct Filter {
     // explicit inverse of the lower-triangular root (arma::inv(arma::trimatl(A)), R/modelTemplate.R:97)
     double rd[N], Ai[TN];
 #pragma unroll
-    for (int i = 0; i < N; i++) rd[i] = 1.0 / A[tri(i, i)];
+    for (int i = 0; i < N; i++) rd[i] = rcp(A[tri(i, i)]);
 #pragma unroll
     for (int j = 0; j < N; j++) {
       Ai[tri(j, j)] = rd[j];
@@ -171,32 +188,81 @@ struct Filter {
   }
 
   // ---- classical RK4, K fixed steps (Boost.odeint integrate_const<runge_kutta4>, rule T1) -------------------
+  // x_{n+1} = x_n + h/6 k1 + h/3 k2 + h/3 k3 + h/6 k4.
+  // -DPSY_RK4_SMEM=1 parks the step's start state x_n and the running sum in shared memory ([element][thread], conflict
+  // free) so that only the stage input lives in registers while the RHS runs.  Measured on B200 (C4, round 1,
+  // profiles/r01_variants.txt): 845 ms vs 722 ms with the compiler's own spilling — slower, so it is OFF by default.
+#ifndef PSY_RK4_SMEM
+#define PSY_RK4_SMEM 0
+#endif
+  static constexpr bool RK4_SMEM = (PSY_RK4_SMEM != 0) && (N >= 4);
+  static constexpr int SMEM_BYTES = RK4_SMEM ? 2 * (N + TN) * PSY_BLOCK * 8 : 0;
   static __device__ __forceinline__ void rk4(const double (&p)[F], double (&m)[N], double (&A)[TN],
                                              const double (&Q)[QLEN], const UT& ut, int person, double h, int K) {
+    if constexpr (RK4_SMEM) {
+      extern __shared__ double psy_smem[];
+      // volatile: the values must really be re-read from shared memory, not forwarded through registers
+      volatile double* sx = psy_smem + threadIdx.x;                       // x_n : sx[e * PSY_BLOCK]
+      volatile double* sa = psy_smem + (N + TN) * PSY_BLOCK + threadIdx.x;  // sum : sa[e * PSY_BLOCK]
 #pragma unroll 1
-    for (int step = 0; step < K; step++) {
-      const double t0 = (double)step * h;
-      double mt[N], At[TN], ma[N], Aa[TN];
+      for (int step = 0; step < K; step++) {
+        const double t0 = (double)step * h;
 #pragma unroll
-      for (int i = 0; i < N; i++) { mt[i] = m[i]; ma[i] = m[i]; }
+        for (int i = 0; i < N; i++) { sx[i * PSY_BLOCK] = m[i]; sa[i * PSY_BLOCK] = m[i]; }
 #pragma unroll
-      for (int i = 0; i < TN; i++) { At[i] = A[i]; Aa[i] = A[i]; }
+        for (int i = 0; i < TN; i++) { sx[(N + i) * PSY_BLOCK] = A[i]; sa[(N + i) * PSY_BLOCK] = A[i]; }
 #pragma unroll 1
-      for (int st = 0; st < 4; st++) {
-        double km[N], kA[TN];
-        const double tc = (st == 0) ? t0 : ((st == 3) ? t0 + h : t0 + 0.5 * h);
-        rhs(p, mt, At, km, kA, Q, ut, person, tc);
-        const double b = (st == 0 || st == 3) ? h * (1.0 / 6.0) : h * (1.0 / 3.0);
-        const double a = (st == 2) ? h : 0.5 * h;
+        for (int st = 0; st < 4; st++) {
+          double km[N], kA[TN];
+          const double tc = (st == 0) ? t0 : ((st == 3) ? t0 + h : t0 + 0.5 * h);
+          rhs(p, m, A, km, kA, Q, ut, person, tc);
+          const double b = (st == 0 || st == 3) ? h * (1.0 / 6.0) : h * (1.0 / 3.0);
+          if (st < 3) {
+            const double a = (st == 2) ? h : 0.5 * h;
 #pragma unroll
-        for (int i = 0; i < N; i++) { ma[i] += b * km[i]; mt[i] = m[i] + a * km[i]; }
+            for (int i = 0; i < N; i++) {
+              sa[i * PSY_BLOCK] = fma(b, km[i], sa[i * PSY_BLOCK]);
+              m[i] = fma(a, km[i], sx[i * PSY_BLOCK]);
+            }
 #pragma unroll
-        for (int i = 0; i < TN; i++) { Aa[i] += b * kA[i]; At[i] = A[i] + a * kA[i]; }
+            for (int i = 0; i < TN; i++) {
+              sa[(N + i) * PSY_BLOCK] = fma(b, kA[i], sa[(N + i) * PSY_BLOCK]);
+              A[i] = fma(a, kA[i], sx[(N + i) * PSY_BLOCK]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < N; i++) m[i] = fma(b, km[i], sa[i * PSY_BLOCK]);
+#pragma unroll
+            for (int i = 0; i < TN; i++) A[i] = fma(b, kA[i], sa[(N + i) * PSY_BLOCK]);
+          }
+        }
       }
+    } else {
+#pragma unroll 1
+      for (int step = 0; step < K; step++) {
+        const double t0 = (double)step * h;
+        double mt[N], At[TN], ma[N], Aa[TN];
 #pragma unroll
-      for (int i = 0; i < N; i++) m[i] = ma[i];
+        for (int i = 0; i < N; i++) { mt[i] = m[i]; ma[i] = m[i]; }
 #pragma unroll
-      for (int i = 0; i < TN; i++) A[i] = Aa[i];
+        for (int i = 0; i < TN; i++) { At[i] = A[i]; Aa[i] = A[i]; }
+#pragma unroll 1
+        for (int st = 0; st < 4; st++) {
+          double km[N], kA[TN];
+          const double tc = (st == 0) ? t0 : ((st == 3) ? t0 + h : t0 + 0.5 * h);
+          rhs(p, mt, At, km, kA, Q, ut, person, tc);
+          const double b = (st == 0 || st == 3) ? h * (1.0 / 6.0) : h * (1.0 / 3.0);
+          const double a = (st == 2) ? h : 0.5 * h;
+#pragma unroll
+          for (int i = 0; i < N; i++) { ma[i] += b * km[i]; mt[i] = m[i] + a * km[i]; }
+#pragma unroll
+          for (int i = 0; i < TN; i++) { Aa[i] += b * kA[i]; At[i] = A[i] + a * kA[i]; }
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) m[i] = ma[i];
+#pragma unroll
+        for (int i = 0; i < TN; i++) A[i] = Aa[i];
+      }
     }
   }
 
@@ -565,6 +631,7 @@ struct Filter {
     if (ii >= L.n_inst) return;
     const PsyInst in = L.inst[ii];
     const int person = in.person;
+    if (person < 0) return;  // warp-alignment padding slot
     // free-slot values of this instance: theta gathered through the person's slot map, one entry shifted by ±eps
     // (setParameterValues_C + setParameterList_C, inst/include/psydiffBasic.h:4-33, 63-121, stateless — quirk Q4)
     double p[F];
@@ -703,9 +770,10 @@ struct Filter {
 
 }  // namespace psy
 
-// psy_module_info = {stepper, srUpdate, nlatent, nmanifest, free slots}: lets the host check a module against its settings
+// psy_module_info = {stepper, srUpdate, nlatent, nmanifest, free slots, dynamic shared memory bytes}: lets the host check a module against its settings
 #define PSY_INSTANTIATE(MODEL)                                                                                      \
-  extern "C" __device__ const int psy_module_info[5] = {MODEL::STEPPER, MODEL::SR ? 1 : 0, MODEL::N, MODEL::M, MODEL::NSLOT}; \
+  extern "C" __device__ const int psy_module_info[6] = {MODEL::STEPPER, MODEL::SR ? 1 : 0, MODEL::N, MODEL::M, MODEL::NSLOT, \
+                                                        MODEL::STEPPER == 0 ? psy::Filter<MODEL>::SMEM_BYTES : 0};           \
   extern "C" __global__ void __launch_bounds__(PSY_BLOCK, PSY_MIN_BLOCKS) psy_filter_kernel(const PsyLaunch L) {   \
     psy::Filter<MODEL>::run(L);                                                                                     \
   }
