@@ -8,3 +8,7 @@ from .model import (  # noqa: F401
     compileParallelGradients, stopParallelGradients, getParameterValues, setParameterValues, clonePsydiffModel,
     sdeModelMatrix, sepNameFromValue, chol2LogChol, extractParameters, makeGroups, checkEquation,
 )
+from .optim import (  # noqa: F401,E402
+    psydiffFitInternal, psydiffGradientsInternal, psydiffOptimBFGS, psydiffOptimNelderMead, psydiffOptimx, extractOptimx,
+    getStandardErrors, GIST, getRegValue, getSubgradients, bestOfN, getDataTemplate, simulateData,
+)

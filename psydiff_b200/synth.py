@@ -177,3 +177,76 @@ def config_c3(N=250_000, T=100, seed=20210131, id_offset=0, **settings):
     )
     kw.update(settings)
     return kw
+
+
+def config_coupled(K=4, N=1000, T=100, seed=20210133, n_groups=8, id_offset=0, **settings):
+    """C5 family: K diffusively coupled Van der Pol oscillators on a ring with all-to-all coupling gains
+    (n = m = 2K; K = 4 is the 8-latent model of config 5, its 12 coupling gains are the lasso targets of the GIST fit).
+    mu_i group-specific as in C4, irregular dt, rk4 with the package default step."""
+    rng = np.random.default_rng(seed)
+    n = 2 * K
+    ids = id_offset + np.arange(1, N + 1)
+    group = ((ids - 1) % n_groups) + 1
+    mu_g = np.linspace(0.6, 1.4, n_groups)[:, None] * np.linspace(0.9, 1.1, K)[None, :]
+    om = np.linspace(0.8, 1.2, K)
+    pairs = [(i, j) for i in range(K) for j in range(K) if i != j]
+    gain = {pr: (0.08 if (pr[1] - pr[0]) % K == 1 else 0.0) for pr in pairs}    # only the ring neighbours are truly coupled
+    ldiff, rsd = 0.1, 0.3
+    m0 = np.array([(1.0 if i % 2 == 0 else 0.0) * (1 - 0.3 * (i // 2)) for i in range(n)])
+    dts = rng.choice([0.5, 0.75, 1.0, 1.25, 1.5], size=(N, T)) + rng.random((N, T)) * 0.1
+    dts[:, 0] = 0.0
+
+    def drift(x, mu):
+        q, v = x[:, 0::2], x[:, 1::2]
+        dx = np.empty_like(x)
+        dx[:, 0::2] = v
+        acc = mu * (1.0 - q * q) * v - (om * om)[None, :] * q
+        for (i, j), g in gain.items():
+            if g:
+                acc[:, i] += g * (q[:, j] - q[:, i])
+        dx[:, 1::2] = acc
+        return dx
+    obs = np.empty((N, T, n))
+    sub = 0.05
+    x = m0[None, :] + 0.5 * rng.standard_normal((N, n))
+    mu = mu_g[group - 1]
+    for t in range(T):
+        rem = dts[:, t].copy()
+        for _ in range(int(np.ceil(rem.max() / sub)) if t > 0 else 0):
+            h = np.minimum(rem, sub)
+            rem -= h
+            k1 = drift(x, mu)
+            k2 = drift(x + h[:, None] * k1, mu)
+            x = x + 0.5 * h[:, None] * (k1 + k2) + ldiff * np.sqrt(h)[:, None] * rng.standard_normal((N, n))
+        obs[:, t, :] = x + rsd * rng.standard_normal((N, n))
+    lines = []
+    parameters = {}
+    for i in range(K):
+        parameters[f"mu{i + 1}"] = float(np.linspace(0.9, 1.1, K)[i])
+        parameters[f"om{i + 1}"] = float(om[i])
+    for (i, j) in pairs:
+        parameters[f"k{i + 1}{j + 1}"] = 0.05
+    for i in range(K):
+        lines.append(f"dx({2 * i}) = x({2 * i + 1});")
+        coup = " + ".join(f"k{i + 1}{j + 1}*(x({2 * j}) - x({2 * i}))" for j in range(K) if j != i)
+        lines.append(f"dx({2 * i + 1}) = mu{i + 1}*(1.0 - x({2 * i})*x({2 * i}))*x({2 * i + 1}) - om{i + 1}*om{i + 1}*x({2 * i}) + {coup};")
+    Lm = np.full((n, n), "0", dtype=object)
+    Rm = np.full((n, n), "0", dtype=object)
+    for i in range(n):
+        Lm[i, i] = f"l{i + 1} = {ldiff}"
+        Rm[i, i] = f"r{i + 1} = {rsd}"
+    kw = dict(
+        dataset={"person": np.repeat(ids, T), "observations": obs.reshape(N * T, n), "dt": dts.reshape(-1)},
+        latentEquations="\n".join(lines), manifestEquations="y = x;", L=Lm, Rchol=Rm, A0=np.eye(n) * 0.5,
+        m0=np.array([[f"m0_{i + 1} = {m0[i]}"] for i in range(n)], dtype=object), parameters=parameters,
+        grouping=" ".join(f"mu{i + 1} | grp;" for i in range(K)),
+        groupingvariables={"grp": (((np.arange(1, id_offset + N + 1) - 1) % n_groups) + 1).astype(float)},
+        integrateFunction="rk4", eps=np.array([1e-6]), direction="central",
+    )
+    kw.update(settings)
+    return kw
+
+
+def config_c5(N=1_000_000, T=100, **settings):
+    """C5: four coupled oscillators (n = m = 8); the 12 coupling gains are lasso-penalised in the GIST fit."""
+    return config_coupled(K=4, N=N, T=T, **settings)

@@ -236,3 +236,17 @@ def test_full_size_c2_properties():
     assert np.array_equal(np.concatenate([halves[0][0], halves[1][0]]), f)
     gv = np.array(list(g.values()))
     assert np.allclose(halves[0][1] + halves[1][1], gv, rtol=1e-7, atol=1e-6 * np.abs(gv).max())
+
+
+@pytest.mark.parametrize("K", [1, 4, 5])
+def test_coupled_oscillator_family_n2_n8_n10(K):
+    """n = 2, 8 (C5's model) and 10 latent states through the same kernel template."""
+    model = pd.newPsydiff(**synth.config_coupled(K=K, N=6, T=8, n_groups=2) if K > 1 else synth.config_c3(N=6, T=8, integrateFunction="rk4"))
+    pd.compileModel(model)
+    fit = pd.fitModel(model)
+    ext = _oracle(model, extended=True).fit(nthreads=8)
+    assert np.isfinite(fit["m2LL"]).all()
+    assert np.max(np.abs(fit["m2LL"] - ext["m2LL"]) / np.abs(ext["m2LL"])) < 1e-10
+    assert np.nanmax(np.abs(fit["latentScores"] - ext["latentScores"])) < 1e-9
+    if K == 4:
+        _check_grad(model, extended=True)
