@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Config 5 of BASELINE.json end to end: GIST lasso fit (R/GIST.R) of the 8-latent coupled-oscillator model with the 12
+coupling gains penalised, followed by a BFGS polish of the unpenalised likelihood (R/optimWrapper.R:23-31), persons
+sharded over all GPUs of the box.
+
+    python examples/c5_gist_fit.py --persons-per-gpu 2048                               # one GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29520 \
+        examples/c5_gist_fit.py --persons-per-gpu 125000                                # C5: N = 1M over 8 x B200
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--persons-per-gpu", type=int, default=2048)
+    ap.add_argument("--timepoints", type=int, default=100)
+    ap.add_argument("--lambda", dest="lam", type=float, default=10.0)
+    ap.add_argument("--outer", type=int, default=15)
+    ap.add_argument("--bfgs-iters", type=int, default=5)
+    a = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    import psydiff_b200 as pd
+    from psydiff_b200 import dist as pdist, optim, synth
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    npg = a.persons_per_gpu
+    model = pd.newPsydiff(**synth.config_c5(N=npg, T=a.timepoints, seed=20210133 + rank, id_offset=rank * npg))
+    if world > 1:
+        pdist.align_parameters(model)
+    pd.compileModel(model)
+    start = pd.getParameterValues(model)
+    gains = [k for k in start if k.startswith("k") and k[1:].isdigit()]
+    t0 = time.time()
+    res = optim.GIST(model, start, lambda_=a.lam * npg * world / 2048, adaptiveLassoWeights={k: 1.0 for k in start},
+                     regularizedParameters=gains, maxIter_out=a.outer, sig=.4, silent=True,
+                     fitTotal=pdist.fitTotalSharded, gradients=pdist.getGradientsSharded)
+    t_gist = time.time() - t0
+    est = pd.getParameterValues(model)
+    names = list(est)
+    t0 = time.time()
+    out = optim.vmmin(np.array(list(est.values())), lambda p: pdist.psydiffFitInternalSharded(p, names, model),
+                      lambda p: pdist.psydiffGradientsInternalSharded(p, names, model), maxit=a.bfgs_iters)
+    t_bfgs = time.time() - t0
+    if rank == 0:
+        r = res["regM2LL"][np.isfinite(res["regM2LL"])]
+        print(json.dumps({
+            "persons": npg * world, "gpus": world, "gist_outer_iterations": int(len(r) - 1), "gist_seconds": t_gist,
+            "seconds_per_outer_iteration": t_gist / max(len(r) - 1, 1), "regM2LL_first": float(r[0]), "regM2LL_last": float(r[-1]),
+            "zeroed_gains": [k for k in gains if est[k] == 0.0], "kept_gains": {k: round(est[k], 4) for k in gains if est[k] != 0.0},
+            "bfgs_iterations": a.bfgs_iters, "bfgs_seconds": t_bfgs, "m2LL_after_bfgs": out["value"]}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -100,3 +100,41 @@ def align_parameters(psydiffModel, label_lists=None, value_lists=None, group=Non
     pt.theta_values = values
     pt._label_pos = pos
     return psydiffModel
+
+
+def fitTotalSharded(psydiffModel, group=None) -> float:
+    """Σ -2LL over ALL persons of all shards (fitModel on every rank + one all-reduce of [Σ, #nonfinite]); NaN if any
+    person of any shard failed — the value psydiffFitInternal tests with anyNA (R/optimWrapper.R:153)."""
+    import torch
+    import torch.distributed as dist
+    from .model import fitModel
+    f = fitModel(psydiffModel)["m2LL"]
+    t = torch.tensor([float(np.nansum(f)), float(np.isnan(f).sum())], dtype=torch.float64,
+                     device="cuda" if torch.cuda.is_available() else "cpu")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    tot, bad = t.tolist()
+    return float("nan") if bad > 0 else tot
+
+
+def psydiffFitInternalSharded(pars, parsnames=None, model=None, group=None) -> float:
+    """psydiffFitInternal (R/optimWrapper.R:146-157) over person shards: identical value on every rank."""
+    import sys
+    from .model import setParameterValues
+    from .optim import _named
+    names, vals = _named(pars, parsnames)
+    setParameterValues(model["pars"]["parameterTable"], vals, names)
+    f = fitTotalSharded(model, group)
+    return .5 * sys.float_info.max if np.isnan(f) else f
+
+
+def psydiffGradientsInternalSharded(pars, parsnames=None, model=None, group=None) -> np.ndarray:
+    """psydiffGradientsInternal (R/optimWrapper.R:167-190) over person shards."""
+    from .model import setParameterValues
+    from .optim import _named
+    names, vals = _named(pars, parsnames)
+    setParameterValues(model["pars"]["parameterTable"], vals, names)
+    g = getGradientsSharded(model, group)
+    out = np.array([g[n] for n in names], dtype=float)
+    out[np.isnan(out)] = 1.0
+    return out

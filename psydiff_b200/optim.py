@@ -224,12 +224,19 @@ def getSubgradients(theta: Dict[str, float], jacobian: Dict[str, float], regIndi
 def GIST(model, startingValues: Dict[str, float], lambda_, adaptiveLassoWeights: Dict[str, float], regularizedParameters,
          eta=1.5, sig=.2, initialStepsize=1.0, stepsizeMin=0.0, stepsizeMax=999999999.0,
          GISTLinesearchCriterion="monotone", GISTNonMonotoneNBack=5, maxIter_out=100, maxIter_in=100, break_outer=1e-8,
-         verbose=0, silent=False, rng: Optional[np.random.Generator] = None):
+         verbose=0, silent=False, rng: Optional[np.random.Generator] = None, fitTotal=None, gradients=None):
     """GIST (R/GIST.R:25-283; Gong et al. 2013): proximal-gradient lasso / adaptive lasso around fitModel + getGradients.
-    ``rng`` drives the reference's random step-size reset (`runif(1) > .9`, R/GIST.R:88); ``rng=None`` disables it."""
+    ``rng`` drives the reference's random step-size reset (`runif(1) > .9`, R/GIST.R:88); ``rng=None`` disables it.
+    ``fitTotal(model) -> Σ-2LL or NaN`` and ``gradients(model) -> dict`` replace fitModel / getGradients when persons are
+    sharded over GPUs (psydiff_b200.dist.fitTotalSharded / getGradientsSharded); every rank then runs the same loop."""
+    getGradients_ = gradients or getGradients
+
     def fit_at(values: Dict[str, float]):
         setParameterValues(model["pars"]["parameterTable"], values)
         try:
+            if fitTotal is not None:
+                tot = fitTotal(model)
+                return None if np.isnan(tot) else float(tot)
             out = fitModel(model)
         except PsydiffError:
             return None
@@ -243,7 +250,7 @@ def GIST(model, startingValues: Dict[str, float], lambda_, adaptiveLassoWeights:
     par_k = getParameterValues(model)
     names = list(par_k.keys())
     grad_km1 = None
-    grad_k = getGradients(model)
+    grad_k = getGradients_(model)
     reg_k = m2LL_k + getRegValue(lambda_, par_k, regularizedParameters, adaptiveLassoWeights)
     regM2LL = np.full(maxIter_out, np.nan)
     regM2LL[0] = reg_k
@@ -296,7 +303,7 @@ def GIST(model, startingValues: Dict[str, float], lambda_, adaptiveLassoWeights:
         if k == maxIter_in and not silent:
             warnings.warn("Maximal number of inner iterations used by GIST. Consider increasing the number of inner iterations.")
         setParameterValues(model["pars"]["parameterTable"], par_kp1)
-        g = getGradients(model)
+        g = getGradients_(model)
         if np.isnan(list(g.values())).any():
             convergence = False
             if not silent:
