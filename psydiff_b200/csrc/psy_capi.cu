@@ -154,7 +154,9 @@ struct psy_model {
   // device
   DevBuf<double> d_obs, d_dt, d_theta, d_f, d_latent, d_pred, d_chunk_part, d_partial;
   DevBuf<int> d_ksteps, d_pid, d_tidx, d_pair_minus, d_pair_base, d_out_idx, d_theta_chunk_off;
-  DevBuf<long long> d_row_off;
+  DevBuf<long long> d_row_off, d_seg_off;
+  DevBuf<int> d_small_list, d_big_list;
+  int64_t n_small = 0, n_big = 0;
   DevBuf<PsyInst> d_inst, d_inst_sub, d_inst_base;
   DevBuf<Chunk> d_chunks;
   int64_t n_inst = 0, n_inst_real = 0, n_chunks = 0;  // n_inst counts padding slots, n_inst_real does not
@@ -211,11 +213,39 @@ __global__ void __launch_bounds__(256) psy_reduce_chunks(const Chunk* __restrict
   if (threadIdx.x < 5) chunk_part[(size_t)blockIdx.x * 5 + threadIdx.x] = sh[threadIdx.x][0];
 }
 
-// one thread per theta (and one for the base pseudo-segment): sequential sum of its chunks' partials
-__global__ void psy_reduce_final(const int* __restrict__ theta_chunk_off, const double* __restrict__ chunk_part, int P,
-                                 double* __restrict__ partial) {
-  const int th = blockIdx.x * blockDim.x + threadIdx.x;
-  if (th > P) return;
+// parameters carried by few persons (person- or small-group-specific, e.g. C3's 250 000 "mu | person" labels): one thread
+// per parameter walks its <= SMALL_SEG entries in order — no chunk stage, still a fixed summation order
+__global__ void psy_reduce_small(const int* __restrict__ small_list, int n_small, const long long* __restrict__ seg_off,
+                                 const int* __restrict__ pair_minus, const int* __restrict__ pair_base,
+                                 const double* __restrict__ f, int P, double* __restrict__ partial) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_small) return;
+  const int th = small_list[q];
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+  for (long long idx = seg_off[th]; idx < seg_off[th + 1]; idx++) {
+    const double f0 = f[pair_base[idx]];
+    const int im = pair_minus[idx];
+    const double fm = f[im], fp = f[im + 1];
+    const double f0s = finite_d(f0) ? f0 : 0.0;
+    a0 += fp - f0s;
+    a1 += fm - f0s;
+    a2 += finite_d(fp) ? 0.0 : 1.0;
+    a3 += finite_d(fm) ? 0.0 : 1.0;
+    a4 += finite_d(f0) ? 0.0 : 1.0;
+  }
+  partial[2 + th] = a0;
+  partial[2 + (size_t)P + th] = a1;
+  partial[2 + 2 * (size_t)P + th] = a2;
+  partial[2 + 3 * (size_t)P + th] = a3;
+  partial[2 + 4 * (size_t)P + th] = a4;
+}
+
+// one thread per chunked parameter (and one for the base pseudo-segment): sequential sum of its chunks' partials
+__global__ void psy_reduce_final(const int* __restrict__ big_list, int n_big, const int* __restrict__ theta_chunk_off,
+                                 const double* __restrict__ chunk_part, int P, double* __restrict__ partial) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_big) return;
+  const int th = big_list[q];
   double a[5] = {0, 0, 0, 0, 0};
   for (int c = theta_chunk_off[th]; c < theta_chunk_off[th + 1]; c++)
     for (int q = 0; q < 5; q++) a[q] += chunk_part[(size_t)c * 5 + q];
@@ -351,7 +381,13 @@ int run_reduction(psy_model* M) {
                                                       M->d_chunk_part.p);
     g_launches++;
   }
-  psy_reduce_final<<<(M->P + 1 + 127) / 128, 128>>>(M->d_theta_chunk_off.p, M->d_chunk_part.p, M->P, M->d_partial.p);
+  if (M->n_small > 0) {
+    psy_reduce_small<<<(unsigned)((M->n_small + 127) / 128), 128>>>(M->d_small_list.p, (int)M->n_small, M->d_seg_off.p, M->d_pair_minus.p,
+                                                                    M->d_pair_base.p, M->d_f.p, M->P, M->d_partial.p);
+    g_launches++;
+  }
+  psy_reduce_final<<<(unsigned)((M->n_big + 127) / 128), 128>>>(M->d_big_list.p, (int)M->n_big, M->d_theta_chunk_off.p, M->d_chunk_part.p,
+                                                                M->P, M->d_partial.p);
   g_launches++;
   CU_TRY(cudaGetLastError());
   return PSY_OK;
@@ -457,7 +493,7 @@ void psy_model_destroy(psy_model* M) {
   if (!M) return;
   M->d_obs.release(); M->d_dt.release(); M->d_theta.release(); M->d_f.release(); M->d_latent.release(); M->d_pred.release();
   M->d_chunk_part.release(); M->d_partial.release(); M->d_ksteps.release(); M->d_pid.release(); M->d_tidx.release();
-  M->d_pair_minus.release(); M->d_pair_base.release(); M->d_out_idx.release(); M->d_theta_chunk_off.release();
+  M->d_pair_minus.release(); M->d_pair_base.release(); M->d_small_list.release(); M->d_big_list.release(); M->d_seg_off.release(); M->d_out_idx.release(); M->d_theta_chunk_off.release();
   M->d_row_off.release(); M->d_inst.release(); M->d_inst_sub.release(); M->d_inst_base.release(); M->d_chunks.release();
   if (M->stage) cudaFreeHost(M->stage);
   if (M->ev0) cudaEventDestroy(M->ev0);
@@ -573,16 +609,21 @@ int psy_set_slots(psy_model* M, int P, const int* tidx) {
   }
   M->h_pair_minus.assign(pair_minus.begin(), pair_minus.begin() + n_pairs);
   // chunk list
-  const int CH = 4096;
+  const int CH = 4096, SMALL_SEG = 64;
   std::vector<Chunk> chunks;
-  std::vector<int> tco(P + 2, 0);
+  std::vector<int> tco(P + 2, 0), small_list, big_list;
   for (int t = 0; t <= P; t++) {
     const int64_t s0 = (t < P) ? M->h_seg_off[t] : n_pairs, s1 = (t < P) ? M->h_seg_off[t + 1] : n_pairs + N;
     tco[t] = (int)chunks.size();
+    if (t < P && s1 - s0 <= SMALL_SEG) { small_list.push_back(t); continue; }
+    big_list.push_back(t);
     for (int64_t s = s0; s < s1; s += CH) chunks.push_back(Chunk{t, (int)s, (int)std::min<int64_t>(CH, s1 - s), 0});
   }
   tco[P + 1] = (int)chunks.size();
   M->n_chunks = (int64_t)chunks.size();
+  M->n_small = (int64_t)small_list.size();
+  M->n_big = (int64_t)big_list.size();
+  std::vector<long long> seg_ll(M->h_seg_off.begin(), M->h_seg_off.end());
   int rc;
   if ((rc = M->d_tidx.upload(M->h_tidx.data(), M->h_tidx.size()))) return rc;
   if ((rc = M->d_inst.upload(inst.data(), inst.size()))) return rc;
@@ -591,6 +632,9 @@ int psy_set_slots(psy_model* M, int P, const int* tidx) {
   if ((rc = M->d_pair_base.upload(pair_base.data(), pair_base.size()))) return rc;
   if ((rc = M->d_chunks.upload(chunks.data(), chunks.size()))) return rc;
   if ((rc = M->d_theta_chunk_off.upload(tco.data(), tco.size()))) return rc;
+  if ((rc = M->d_small_list.upload(small_list.data(), small_list.size()))) return rc;
+  if ((rc = M->d_big_list.upload(big_list.data(), big_list.size()))) return rc;
+  if ((rc = M->d_seg_off.upload(seg_ll.data(), seg_ll.size()))) return rc;
   if ((rc = M->d_chunk_part.alloc(chunks.size() * 5))) return rc;
   if ((rc = M->d_partial.alloc(5 * (size_t)P + 2))) return rc;
   if ((rc = M->d_f.alloc((size_t)M->n_inst))) return rc;
