@@ -146,10 +146,9 @@ struct psy_model {
   std::vector<int> h_tidx;           // N x F
   std::vector<int64_t> h_inst_off;   // N+1 (end of each person's possibly padded block)
   std::vector<int64_t> h_inst_start; // N first instance (= base instance) of each person
-  std::vector<int> h_dl;             // distinct theta lists, flattened at (inst_off[p]-p... ) see set_slots
+  std::vector<int> h_dl;             // distinct theta of each person in slot order, flattened (see psy_set_slots)
   std::vector<int64_t> h_dl_off;     // N+1
   std::vector<int64_t> h_seg_off;    // P+1 (pairs per theta)
-  std::vector<int> h_pair_minus;     // instance index of the (p, theta, -) instance, sorted by theta then person
   double ksteps_h = -1.0;
   // device
   DevBuf<double> d_obs, d_dt, d_theta, d_f, d_latent, d_pred, d_chunk_part, d_partial;
@@ -607,7 +606,6 @@ int psy_set_slots(psy_model* M, int P, const int* tidx) {
     pair_minus[n_pairs + p] = (int)o;  // base pseudo-segment (theta == P)
     pair_base[n_pairs + p] = (int)o;
   }
-  M->h_pair_minus.assign(pair_minus.begin(), pair_minus.begin() + n_pairs);
   // chunk list
   const int CH = 4096, SMALL_SEG = 64;
   std::vector<Chunk> chunks;

@@ -9,9 +9,8 @@ from __future__ import annotations
 
 import copy
 import ctypes as C
-import re
 import warnings
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Sequence
 
 import numpy as np
 
