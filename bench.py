@@ -117,11 +117,12 @@ def cpu_sample(args, model, steps=1, warmup=0):
     ts = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        orc.gradients(nthreads=cores, persons=persons)
+        res = orc.gradients(nthreads=cores, persons=persons)
         if i >= warmup:
             ts.append(time.perf_counter() - t0)
     sec = sum(ts) / len(ts)
     T = args.timepoints
+    cpu_sample.last = {"persons": persons, "m2LL": res["m2LL"], "grad": res["grad_clean"]}
     return n * T / sec, cores, (f"first {n} persons of the C4 shard x T={T}, -2LL + full central FD gradient "
                                 f"(61 filter sweeps/person), {cores} threads"), sec
 
@@ -283,9 +284,16 @@ def main():
             "hbm_algorithmic_bytes": int(obs_host.nbytes + dtv.nbytes + 8 * n_inst),
         },
     }
+    gvals = np.array(list(g.values()))
+    line["check"] = {"m2ll_total": total, "finite": bool(np.isfinite(total) and np.isfinite(gvals).all())}
     if world == 1 and not args.no_cpu_baseline:
         val, cores, desc, sec = cpu_sample(args, model)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "seconds": sec}
+        # the CPU sample doubles as a parity spot check of the timed GPU path on the very same inputs
+        ref = cpu_sample.last
+        gpu = pd.fitModel(model, states=False)["m2LL"][ref["persons"]]
+        line["check"]["m2ll_vs_oracle_max_rel"] = float(np.max(np.abs(gpu - ref["m2LL"]) / np.abs(ref["m2LL"])))
+        line["check"]["oracle_persons"] = int(len(ref["persons"]))
     print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist

@@ -108,7 +108,7 @@ def fitTotalSharded(psydiffModel, group=None) -> float:
     import torch
     import torch.distributed as dist
     from .model import fitModel
-    f = fitModel(psydiffModel)["m2LL"]
+    f = fitModel(psydiffModel, states=False)["m2LL"]
     t = torch.tensor([float(np.nansum(f)), float(np.isnan(f).sum())], dtype=torch.float64,
                      device="cuda" if torch.cuda.is_available() else "cpu")
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

@@ -470,8 +470,9 @@ def clonePsydiffModel(model):
     return copy.deepcopy(model)
 
 
-def fitModel(psydiffModel, skipUpdate: bool = False):
+def fitModel(psydiffModel, skipUpdate: bool = False, states: bool = True):
     """fitModel (R/modelTemplate.R:165-420): per-person -2LL, latentScores, predictedManifest.
+    ``states=False`` (not in the reference) skips the two rows x n / rows x m output matrices — 2x the input bytes.
 
     Like the reference it overwrites model$m2LL / $latentScores / $predictedManifest in place and clears the
     ``changed`` flags (R/modelTemplate.R:410-414).  Every person is evaluated on every call (stateless parameter
@@ -482,13 +483,18 @@ def fitModel(psydiffModel, skipUpdate: bool = False):
     N = pt.theta_index.shape[0]
     rows = psydiffModel["data"]["observations"].shape[0]
     m2ll = np.empty(N)
-    lat = np.empty((rows, psydiffModel["nlatent"]), order="F")
-    pred = np.empty((rows, psydiffModel["nmanifest"]), order="F")
+    if states:
+        lat = np.empty((rows, psydiffModel["nlatent"]), order="F")
+        pred = np.empty((rows, psydiffModel["nmanifest"]), order="F")
+    else:
+        lat = pred = None
     _lib.check(_lib.lib().psy_fit(h.ptr, _lib.dptr(theta) if len(theta) else None, 1 if skipUpdate else 0, _lib.dptr(m2ll),
-                                  lat.ctypes.data_as(_lib.c_double_p), pred.ctypes.data_as(_lib.c_double_p)))
+                                  lat.ctypes.data_as(_lib.c_double_p) if states else None,
+                                  pred.ctypes.data_as(_lib.c_double_p) if states else None))
     psydiffModel["m2LL"] = m2ll
-    psydiffModel["latentScores"] = lat
-    psydiffModel["predictedManifest"] = pred
+    if states:
+        psydiffModel["latentScores"] = lat
+        psydiffModel["predictedManifest"] = pred
     pt.changed[:] = False
     return {"latentScores": lat, "predictedManifest": pred, "m2LL": m2ll}
 
