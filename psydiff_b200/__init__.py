@@ -9,6 +9,6 @@ from .model import (  # noqa: F401
     sdeModelMatrix, sepNameFromValue, chol2LogChol, extractParameters, makeGroups, checkEquation,
 )
 from .optim import (  # noqa: F401,E402
-    psydiffFitInternal, psydiffGradientsInternal, psydiffOptimBFGS, psydiffOptimNelderMead, psydiffOptimx, extractOptimx,
+    psydiffFitInternal, psydiffGradientsInternal, psydiffOptimBFGS, psydiffOptimNelderMead, psydiffOptimx, extractOptimx, psydiffDEoptim, psydiffSubplex, psydiffNLopt,
     getStandardErrors, GIST, getRegValue, getSubgradients, bestOfN, getDataTemplate, simulateData,
 )

@@ -21,6 +21,7 @@
 #include <fstream>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 #include <sys/stat.h>
@@ -525,12 +526,24 @@ int psy_upload(psy_model* M, int64_t rows, int N, const double* obs_cm, const do
     M->stage_n = cnt;
   }
   double* rm = M->stage;
-  const int64_t RB = 4096;
-  for (int64_t r0 = 0; r0 < rows; r0 += RB) {
-    const int64_t r1 = std::min(rows, r0 + RB);
-    for (int j = 0; j < m; j++) {
-      const double* col = obs_cm + (size_t)j * rows;
-      for (int64_t r = r0; r < r1; r++) rm[(size_t)r * m + j] = col[r];
+  {
+    const int64_t RB = 4096;
+    const int64_t nblk = (rows + RB - 1) / RB;
+    const int nth = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), (int64_t)16, nblk / 8}));
+    auto work = [&](int t) {
+      for (int64_t b = t; b < nblk; b += nth) {
+        const int64_t r0 = b * RB, r1 = std::min(rows, r0 + RB);
+        for (int j = 0; j < m; j++) {
+          const double* col = obs_cm + (size_t)j * rows;
+          for (int64_t r = r0; r < r1; r++) rm[(size_t)r * m + j] = col[r];
+        }
+      }
+    };
+    if (nth == 1) work(0);
+    else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nth; t++) th.emplace_back(work, t);
+      for (auto& x : th) x.join();
     }
   }
   int rc;

@@ -164,6 +164,34 @@ def psydiffOptimx(model, method=("Nelder-Mead", "BFGS"), fn=psydiffFitInternal, 
     return {"class": "optimx", "start": start, "rows": rows}
 
 
+def psydiffDEoptim(model, lower, upper, control: Optional[dict] = None):
+    """psydiffDEoptim (R/optimWrapper.R:83-92): pass-through to a library differential-evolution optimiser (scipy here)."""
+    from scipy.optimize import differential_evolution
+    control = control or {}
+    names = list(getParameterValues(model).keys())
+    res = differential_evolution(lambda p: psydiffFitInternal(p, names, model), list(zip(lower, upper)),
+                                 maxiter=int(control.get("itermax", 200)), seed=control.get("seed"), polish=False)
+    return {"optim": {"bestmem": dict(zip(names, res.x)), "bestval": float(res.fun), "nfeval": res.nfev, "iter": res.nit}}
+
+
+def psydiffSubplex(model, control: Optional[dict] = None):
+    """psydiffSubplex (R/optimWrapper.R:102-111).  No subplex implementation ships in this image; the derivative-free
+    simplex search it decomposes into (Nelder-Mead) is used on the full parameter vector instead."""
+    return psydiffOptimNelderMead(model, control)
+
+
+def psydiffNLopt(model, eval_f=psydiffFitInternal, control: Optional[dict] = None):
+    """psydiffNLopt (R/optimWrapper.R:121-136): the reference asks nloptr for NLOPT_LD_LBFGS; here scipy's L-BFGS-B with
+    the batched finite-difference gradient."""
+    from scipy.optimize import minimize
+    control = control or {}
+    start = getParameterValues(model)
+    names = list(start.keys())
+    res = minimize(lambda p: eval_f(p, names, model), np.array(list(start.values())), jac=lambda p: psydiffGradientsInternal(p, names, model),
+                   method="L-BFGS-B", options={"maxfun": int(control.get("maxeval", 500))})
+    return {"solution": dict(zip(names, res.x)), "objective": float(res.fun), "iterations": res.nit, "status": int(res.status)}
+
+
 def extractOptimx(model, opt):
     """extractOptimx (R/optimWrapper.R:57-72): write the best optimiser's parameters into the model (not refitted)."""
     if not (isinstance(opt, dict) and opt.get("class") == "optimx"):
