@@ -289,6 +289,11 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         val, cores, desc, sec = cpu_sample(args, model)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "seconds": sec}
+        # the reference's fitModel itself is serial (R/modelTemplate.R:244): same port on ONE thread, one person
+        from oracle.oracle import Oracle
+        t1 = time.perf_counter()
+        Oracle(model).gradients(nthreads=1, persons=np.arange(1))
+        line["cpu_baseline"]["single_thread_value"] = args.timepoints / (time.perf_counter() - t1)
         # the CPU sample doubles as a parity spot check of the timed GPU path on the very same inputs
         ref = cpu_sample.last
         gpu = pd.fitModel(model, states=False)["m2LL"][ref["persons"]]

@@ -283,3 +283,38 @@ def test_sharded_api_on_one_rank_equals_getGradients():
     assert a == b
     assert tot == pytest.approx(float(pd.fitModel(model)["m2LL"].sum()), rel=1e-13)
     assert pdist.fitTotalSharded(model) == pytest.approx(tot, rel=1e-13)
+
+
+def test_edge_cases_single_row_all_missing_person_and_abi_errors():
+    import ctypes as C
+    from psydiff_b200 import _lib
+    # one person with a single time point (dt = 0: no integration at all), one person with every observation missing
+    kw = synth.config_c1(N=3, T=6, seed=13)
+    d = kw["dataset"]
+    keep = np.r_[0, np.arange(6, 18)]                      # person 1 keeps only its first row
+    d = {k: v[keep] for k, v in d.items()}
+    d["observations"][1:7] = np.nan                          # person 2: nothing observed
+    kw["dataset"] = d
+    model = pd.newPsydiff(**kw)
+    fit, ref = _check_fit(model)
+    assert fit["m2LL"][1] == 0.0 and np.isfinite(fit["m2LL"]).all()
+    # with no update the latent scores of person 2 are the pure prediction
+    _check_grad(model)
+    # C-ABI argument errors are return codes with a message, never a crash
+    L, h = _lib.lib(), model["_handle"].ptr
+    theta = np.ascontiguousarray(model["pars"]["parameterTable"].theta_values)
+    bad_idx = np.full(model["pars"]["parameterTable"].theta_index.shape, 99, dtype=np.int32)
+    assert L.psy_set_slots(h, len(theta), _lib.iptr(bad_idx)) == 1 and b"out of range" in L.psy_last_error()
+    good = np.ascontiguousarray(model["pars"]["parameterTable"].theta_index, dtype=np.int32)
+    assert L.psy_set_slots(h, len(theta), _lib.iptr(good)) == 0
+    obs = np.asfortranarray(d["observations"])
+    off = np.array([0, 1, 7, 12], dtype=np.int64)            # does not end at rows
+    pid = np.array([1, 2, 3], dtype=np.int32)
+    assert L.psy_upload(h, obs.shape[0], 3, obs.ctypes.data_as(_lib.c_double_p), _lib.dptr(d["dt"]), _lib.i64ptr(off), _lib.iptr(pid)) == 1
+    g = np.zeros(len(theta))
+    eps = np.array([1e-6])
+    assert L.psy_gradients(h, _lib.dptr(theta), _lib.dptr(eps), 1, 7, _lib.dptr(g), None) == 1
+    assert b"Unknown direction" in L.psy_last_error()
+    model["direction"] = "sideways"
+    with pytest.raises(pd.PsydiffError, match="Unknown direction"):
+        pd.getGradients(model)
