@@ -29,7 +29,7 @@ def _check_fit(model, states=True, skipUpdate=False):
     if skipUpdate:
         assert np.all(fit["m2LL"] == 0.0)
     else:
-        rel = np.abs(fit["m2LL"][fin] - ref["m2LL"][fin]) / np.abs(ref["m2LL"][fin])
+        rel = np.abs(fit["m2LL"][fin] - ref["m2LL"][fin]) / np.maximum(np.abs(ref["m2LL"][fin]), 1e-300)   # 0 vs 0 -> 0
         assert rel.max() < M2LL_RTOL, rel.max()
     if states:
         scale = max(1.0, np.nanmax(np.abs(ref["latentScores"])))
