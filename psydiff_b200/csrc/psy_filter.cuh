@@ -37,9 +37,6 @@
 #ifndef PSY_MIN_BLOCKS
 #define PSY_MIN_BLOCKS 1
 #endif
-#ifndef PSY_RHS_VARIANT
-#define PSY_RHS_VARIANT 0  // 0 = A (explicit inverse, G stored), 1 = B (forward substitution), 2 = C (fused accumulation)
-#endif
 
 namespace psy {
 
@@ -73,7 +70,7 @@ struct Filter {
   struct UT { double sqrtc, wm0, wm1, wc0, wc1, kap; };
 
   // ---- RHS of the reduced sigma-point ODE (replaces odeintModel::operator() + getMMatrix) -------------------
-  static __device__ __forceinline__ void rhs_inv(const double (&p)[F], const double (&m)[N], const double (&A)[TN],
+  static __device__ __forceinline__ void rhs(const double (&p)[F], const double (&m)[N], const double (&A)[TN],
                                              double (&dm)[N], double (&dA)[TN], const double (&Q)[QLEN],
                                              const UT& ut, int person, double t) {
     // explicit inverse of the lower-triangular root (arma::inv(arma::trimatl(A)), R/modelTemplate.R:97)
@@ -190,255 +187,16 @@ struct Filter {
       }
   }
 
-  // Variant B of the RHS (-DPSY_RHS_VARIANT=1): the diffusion term A⁻¹ L Lᵀ A⁻ᵀ is formed first (A⁻¹ is dead afterwards),
-  // then every column of G = A⁻¹ D is obtained by forward substitution with A itself and folded straight into
-  // Phi's lower triangle — G is never stored and A⁻¹ does not stay live across the column loop (≈ 45 fewer live doubles).
-  static __device__ __forceinline__ void rhs_solve(const double (&p)[F], const double (&m)[N], const double (&A)[TN],
-                                                   double (&dm)[N], double (&dA)[TN], const double (&Q)[QLEN],
-                                                   const UT& ut, int person, double t) {
-    double rd[N], Ph[TN];
-#pragma unroll
-    for (int i = 0; i < N; i++) rd[i] = rcp(A[tri(i, i)]);
-    {
-      double Ai[TN];
-#pragma unroll
-      for (int j = 0; j < N; j++) {
-        Ai[tri(j, j)] = rd[j];
-#pragma unroll
-        for (int i = j + 1; i < N; i++) {
-          double acc = A[tri(i, j)] * rd[j];
-#pragma unroll
-          for (int k = j + 1; k < i; k++) acc += A[tri(i, k)] * Ai[tri(k, j)];
-          Ai[tri(i, j)] = -acc * rd[i];
-        }
-      }
-      if constexpr (Mdl::L_STRUCT == L_DIAG) {
-        double Bq[TN];
-#pragma unroll
-        for (int i = 0; i < N; i++)
-#pragma unroll
-          for (int k = 0; k <= i; k++) Bq[tri(i, k)] = Ai[tri(i, k)] * Q[k];
-#pragma unroll
-        for (int i = 0; i < N; i++)
-#pragma unroll
-          for (int j = 0; j <= i; j++) {
-            double acc = Bq[tri(i, 0)] * Ai[tri(j, 0)];
-#pragma unroll
-            for (int k = 1; k <= j; k++) acc += Bq[tri(i, k)] * Ai[tri(j, k)];
-            Ph[tri(i, j)] = acc;
-          }
-      } else {
-        double Z[N * N];
-#pragma unroll
-        for (int i = 0; i < N; i++)
-#pragma unroll
-          for (int j = 0; j < N; j++) {
-            double acc = 0.0;
-#pragma unroll
-            for (int k = 0; k <= i; k++) acc += Ai[tri(i, k)] * ((k >= j) ? Q[tri(k, j)] : Q[tri(j, k)]);
-            Z[i + j * N] = acc;
-          }
-#pragma unroll
-        for (int i = 0; i < N; i++)
-#pragma unroll
-          for (int j = 0; j <= i; j++) {
-            double acc = 0.0;
-#pragma unroll
-            for (int k = 0; k <= j; k++) acc += Z[i + k * N] * Ai[tri(j, k)];
-            Ph[tri(i, j)] = acc;
-          }
-      }
-    }
-    Vec<N> xc, f0;
-#pragma unroll
-    for (int i = 0; i < N; i++) { xc.v[i] = m[i]; f0.v[i] = 0.0; }
-    Mdl::latentEquation(xc, f0, p, person, t);
-#pragma unroll
-    for (int i = 0; i < N; i++) dm[i] = ut.wm0 * f0.v[i];
-#pragma unroll
-    for (int j = 0; j < N; j++) {
-      Vec<N> xp, xm, fp, fm;
-#pragma unroll
-      for (int i = 0; i < N; i++) {
-        if (i >= j) {
-          xp.v[i] = fma(ut.sqrtc, A[tri(i, j)], m[i]);
-          xm.v[i] = fma(-ut.sqrtc, A[tri(i, j)], m[i]);
-        } else {
-          xp.v[i] = m[i];
-          xm.v[i] = m[i];
-        }
-        fp.v[i] = 0.0;
-        fm.v[i] = 0.0;
-      }
-      Mdl::latentEquation(xp, fp, p, person, t);
-      Mdl::latentEquation(xm, fm, p, person, t);
-      double g[N];
-#pragma unroll
-      for (int i = 0; i < N; i++) {
-        dm[i] = fma(ut.wm1, fp.v[i] + fm.v[i], dm[i]);
-        double acc = fp.v[i] - fm.v[i];
-#pragma unroll
-        for (int k = 0; k < i; k++) acc -= A[tri(i, k)] * g[k];
-        g[i] = acc * rd[i];
-      }
-      // M += kap (G + Gᵀ): column j of G touches row j (i < j) and column j (i >= j) of the lower triangle
-#pragma unroll
-      for (int i = 0; i < N; i++) {
-        if (i >= j) Ph[tri(i, j)] = fma(ut.kap, g[i], Ph[tri(i, j)]);
-        if (i <= j) Ph[tri(j, i)] = fma(ut.kap, g[i], Ph[tri(j, i)]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < N; i++) Ph[tri(i, i)] *= 0.5;  // getPhi_C: halved diagonal
-#pragma unroll
-    for (int i = 0; i < N; i++)
-#pragma unroll
-      for (int j = 0; j <= i; j++) {
-        double acc = A[tri(i, j)] * Ph[tri(j, j)];
-#pragma unroll
-        for (int k = j + 1; k <= i; k++) acc += A[tri(i, k)] * Ph[tri(k, j)];
-        dA[tri(i, j)] = acc;
-      }
-  }
-
-  // Variant C of the RHS (-DPSY_RHS_VARIANT=2; fewer instructions but more spills, measured slower): like variant A it uses the explicit inverse (independent dot products, best ILP),
-  // but A⁻¹ is pre-scaled by kap once and every G_ij = Σ_k A⁻¹_ik d_k is accumulated by FMA chains straight INTO the
-  // entry of M's lower triangle it belongs to (seeded with the diffusion term): no first-term multiplies, no G storage,
-  // no G + Gᵀ adds — 57 fewer FP64 instructions per evaluation at n = 6.
-  static __device__ __forceinline__ void rhs_fused(const double (&p)[F], const double (&m)[N], const double (&A)[TN],
-                                                   double (&dm)[N], double (&dA)[TN], const double (&Q)[QLEN],
-                                                   const UT& ut, int person, double t) {
-    double rd[N], Ai[TN], Ph[TN];
-#pragma unroll
-    for (int i = 0; i < N; i++) rd[i] = rcp(A[tri(i, i)]);
-#pragma unroll
-    for (int j = 0; j < N; j++) {
-      Ai[tri(j, j)] = rd[j];
-#pragma unroll
-      for (int i = j + 1; i < N; i++) {
-        double acc = A[tri(i, j)] * rd[j];
-#pragma unroll
-        for (int k = j + 1; k < i; k++) acc += A[tri(i, k)] * Ai[tri(k, j)];
-        Ai[tri(i, j)] = -acc * rd[i];
-      }
-    }
-    // Ph <- lower(A⁻¹ L Lᵀ A⁻ᵀ)
-    if constexpr (Mdl::L_STRUCT == L_DIAG) {
-      double Bq[TN];
-#pragma unroll
-      for (int i = 0; i < N; i++)
-#pragma unroll
-        for (int k = 0; k <= i; k++) Bq[tri(i, k)] = Ai[tri(i, k)] * Q[k];
-#pragma unroll
-      for (int i = 0; i < N; i++)
-#pragma unroll
-        for (int j = 0; j <= i; j++) {
-          double acc = Bq[tri(i, 0)] * Ai[tri(j, 0)];
-#pragma unroll
-          for (int k = 1; k <= j; k++) acc += Bq[tri(i, k)] * Ai[tri(j, k)];
-          Ph[tri(i, j)] = acc;
-        }
-    } else {
-      double Z[N * N];
-#pragma unroll
-      for (int i = 0; i < N; i++)
-#pragma unroll
-        for (int j = 0; j < N; j++) {
-          double acc = 0.0;
-#pragma unroll
-          for (int k = 0; k <= i; k++) acc += Ai[tri(i, k)] * ((k >= j) ? Q[tri(k, j)] : Q[tri(j, k)]);
-          Z[i + j * N] = acc;
-        }
-#pragma unroll
-      for (int i = 0; i < N; i++)
-#pragma unroll
-        for (int j = 0; j <= i; j++) {
-          double acc = 0.0;
-#pragma unroll
-          for (int k = 0; k <= j; k++) acc += Z[i + k * N] * Ai[tri(j, k)];
-          Ph[tri(i, j)] = acc;
-        }
-    }
-    // A⁻¹ <- kap A⁻¹ (only used for G from here on)
-#pragma unroll
-    for (int i = 0; i < TN; i++) Ai[i] *= ut.kap;
-    Vec<N> xc, f0;
-#pragma unroll
-    for (int i = 0; i < N; i++) { xc.v[i] = m[i]; f0.v[i] = 0.0; }
-    Mdl::latentEquation(xc, f0, p, person, t);
-#pragma unroll
-    for (int i = 0; i < N; i++) dm[i] = ut.wm0 * f0.v[i];
-#pragma unroll
-    for (int j = 0; j < N; j++) {
-      Vec<N> xp, xm, fp, fm;
-#pragma unroll
-      for (int i = 0; i < N; i++) {
-        if (i >= j) {
-          xp.v[i] = fma(ut.sqrtc, A[tri(i, j)], m[i]);
-          xm.v[i] = fma(-ut.sqrtc, A[tri(i, j)], m[i]);
-        } else {
-          xp.v[i] = m[i];
-          xm.v[i] = m[i];
-        }
-        fp.v[i] = 0.0;
-        fm.v[i] = 0.0;
-      }
-      Mdl::latentEquation(xp, fp, p, person, t);
-      Mdl::latentEquation(xm, fm, p, person, t);
-      double d[N];
-#pragma unroll
-      for (int i = 0; i < N; i++) {
-        dm[i] = fma(ut.wm1, fp.v[i] + fm.v[i], dm[i]);
-        d[i] = fp.v[i] - fm.v[i];
-      }
-      // kap G_ij = Σ_{k<=i} (kap A⁻¹)_ik d_k goes to M[i][j] (i >= j) or M[j][i] (i < j); the diagonal gets it twice
-#pragma unroll
-      for (int i = 0; i < N; i++) {
-        const int e = (i >= j) ? tri(i, j) : tri(j, i);
-        double acc = Ph[e];
-#pragma unroll
-        for (int k = 0; k <= i; k++) acc = fma(Ai[tri(i, k)], d[k], acc);
-        if (i == j) {
-#pragma unroll
-          for (int k = 0; k <= i; k++) acc = fma(Ai[tri(i, k)], d[k], acc);
-        }
-        Ph[e] = acc;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < N; i++) Ph[tri(i, i)] *= 0.5;  // getPhi_C: halved diagonal
-#pragma unroll
-    for (int i = 0; i < N; i++)
-#pragma unroll
-      for (int j = 0; j <= i; j++) {
-        double acc = A[tri(i, j)] * Ph[tri(j, j)];
-#pragma unroll
-        for (int k = j + 1; k <= i; k++) acc += A[tri(i, k)] * Ph[tri(k, j)];
-        dA[tri(i, j)] = acc;
-      }
-  }
-
-  static __device__ __forceinline__ void rhs(const double (&p)[F], const double (&m)[N], const double (&A)[TN],
-                                             double (&dm)[N], double (&dA)[TN], const double (&Q)[QLEN],
-                                             const UT& ut, int person, double t) {
-#if PSY_RHS_VARIANT == 0
-    rhs_inv(p, m, A, dm, dA, Q, ut, person, t);
-#elif PSY_RHS_VARIANT == 1
-    rhs_solve(p, m, A, dm, dA, Q, ut, person, t);
-#else
-    rhs_fused(p, m, A, dm, dA, Q, ut, person, t);
-#endif
-  }
-
   // ---- classical RK4, K fixed steps (Boost.odeint integrate_const<runge_kutta4>, rule T1) -------------------
   // x_{n+1} = x_n + h/6 k1 + h/3 k2 + h/3 k3 + h/6 k4.
-  // -DPSY_RK4_SMEM=1 parks the step's start state x_n and the running sum in shared memory ([element][thread], conflict
-  // free) so that only the stage input lives in registers while the RHS runs.  Measured on B200 (C4, round 1,
-  // profiles/r01_variants.txt): 845 ms vs 722 ms with the compiler's own spilling — slower, so it is OFF by default.
+  // For N >= 7 the step's start state x_n and the running sum are parked in shared memory ([element][thread], conflict
+  // free; loads batched before the arithmetic, stores after) so that only the stage input lives in registers while the
+  // RHS runs.  Measured on B200 (profiles/r01_variants.txt): n = 8: 1167 -> 1096 ms; n = 6: 722 -> 762 ms, i.e. the
+  // compiler's own spill placement wins as long as the state nearly fits, hence the threshold.  -DPSY_RK4_SMEM=0/1 overrides.
 #ifndef PSY_RK4_SMEM
-#define PSY_RK4_SMEM 0
+#define PSY_RK4_SMEM (-1)
 #endif
-  static constexpr bool RK4_SMEM = (PSY_RK4_SMEM != 0) && (N >= 4);
+  static constexpr bool RK4_SMEM = (PSY_RK4_SMEM == 1) || (PSY_RK4_SMEM == -1 && N >= 7);
   static constexpr int SMEM_BYTES = RK4_SMEM ? 2 * (N + TN) * PSY_BLOCK * 8 : 0;
   static __device__ __forceinline__ void rk4(const double (&p)[F], double (&m)[N], double (&A)[TN],
                                              const double (&Q)[QLEN], const UT& ut, int person, double h, int K) {
