@@ -1,0 +1,150 @@
+"""A second, independent restatement of the reference's SR-UKF path in numpy — TEST INFRASTRUCTURE ONLY.
+
+Purpose: cross-check oracle/psy_oracle.cpp with an implementation that shares no code with it and that gets its dense
+linear algebra from a real LAPACK (numpy.linalg.qr / inv / cholesky), the way the reference gets it from Armadillo.
+In particular it confirms SURVEY §8c T3 (the sign convention of LAPACK's QR does not leak through cholupdate).
+Written function by function after inst/include/psydiffInternals.h and R/modelTemplate.R; pure Python loops, so only
+for tiny cases.  Drift / measurement equations are passed as Python callables f(x, pars, person, t).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+DBL_EPS = np.finfo(float).eps
+
+
+def getSigmaPoints(m, A, c):                       # psydiffInternals.h:4-16 (covarianceIsRoot = TRUE)
+    n = len(m)
+    X = np.zeros((n, 2 * n + 1))
+    X[:, 1:n + 1] = np.sqrt(c) * A
+    X[:, n + 1:] = -1 * np.sqrt(c) * A
+    return X + m[:, None]
+
+
+def getMeanWeights(n, alpha, beta, kappa):         # :18-24
+    lam = alpha ** 2 * (n + kappa) - n
+    w = np.full(2 * n + 1, 1 / (2 * (n + lam)))
+    w[0] = lam / (n + lam)
+    return w
+
+
+def getCovWeights(n, alpha, beta, kappa):          # :26-33
+    lam = alpha ** 2 * (n + kappa) - n
+    w = np.full(2 * n + 1, 1 / (2 * (n + lam)))
+    w[0] = lam / (n + lam) + (1 - alpha ** 2 + beta)
+    return w
+
+
+def getWMatrix(wm, wc):                            # :35-44
+    D = np.eye(len(wm)) - wm[:, None]
+    return D @ np.diag(wc) @ D.T
+
+
+def getAFromSigmaPoints(X, wm, c):                 # :51-60
+    n = X.shape[0]
+    return (X[:, 1:n + 1] - (X @ wm)[:, None]) / np.sqrt(c)
+
+
+def getPhi(M):                                     # :69-75
+    P = np.tril(M)
+    P[np.diag_indices_from(P)] = .5 * np.diag(M)
+    return P
+
+
+def cholupdate(L, x, v, direction):                # :133-165
+    L, x = L.copy(), x.copy()
+    d = {"update": 1, "downdate": -1}[direction]
+    v = abs(v) ** .25
+    x = v * x
+    n = len(x)
+    for k in range(n):
+        r = np.sqrt(L[k, k] ** 2 + d * x[k] ** 2)
+        c, s = r / L[k, k], x[k] / L[k, k]
+        L[k, k] = r
+        if k < n - 1:
+            L[k + 1:, k] = (L[k + 1:, k] + d * s * x[k + 1:]) / c
+            x[k + 1:] = c * x[k + 1:] - s * L[k + 1:, k]
+    return L
+
+
+def predictSquareRootOfS(Y, mu, Rchol, wc0, wc1):  # :174-198, qr_C :167-171 through LAPACK
+    T = np.hstack([np.sqrt(wc1) * (Y - mu[:, None]), Rchol])
+    R = np.linalg.qr(T.T, mode="r")
+    srS = R.T.copy()
+    srS = cholupdate(srS, Y[:, 0] - mu, abs(wc0), "downdate" if wc0 < 0 else "update")
+    return np.tril(srS)
+
+
+def m2ll_chol(nobs, raw, mean, srS):               # :117-131
+    ci = np.linalg.inv(np.tril(srS))
+    r = raw - mean
+    return nobs * np.log(2 * np.pi) + 2 * np.sum(np.log(np.diag(srS))) + float(r @ ci.T @ ci @ r)
+
+
+def rhs(X, t, drift, pars, person, wm, wc, c, L):  # odeintModel::operator() + getMMatrix, R/modelTemplate.R:85-163
+    n, s = X.shape
+    A = getAFromSigmaPoints(X, wm, c)
+    Ainv = np.linalg.inv(np.tril(A))
+    F = np.column_stack([drift(X[:, i], pars, person, t) for i in range(s)])
+    mx, mf = X @ wm, F @ wm
+    s1 = sum(wc[i] * np.outer(X[:, i] - mx, F[:, i] - mf) for i in range(s))
+    s2 = sum(wc[i] * np.outer(F[:, i] - mf, X[:, i] - mx) for i in range(s))
+    M = Ainv @ (s1 + s2 + L @ np.eye(n) @ L.T) @ Ainv.T
+    APhi = A @ getPhi(M)
+    aug = np.zeros_like(X)
+    aug[:, 1:n + 1] = APhi
+    aug[:, n + 1:] = -1 * APhi
+    return mf[:, None] + np.sqrt(c) * aug
+
+
+def integrate_const_rk4(X, t1, h, f):              # Boost.odeint integrate_const<runge_kutta4>, rule T1
+    step, time = 0, 0.0
+    while (time + h) - t1 <= DBL_EPS:
+        k1 = f(X, time)
+        k2 = f(X + h / 2 * k1, time + h / 2)
+        k3 = f(X + h / 2 * k2, time + h / 2)
+        k4 = f(X + h * k3, time + h)
+        X = X + h / 6 * k1 + h / 3 * k2 + h / 3 * k3 + h / 6 * k4
+        step += 1
+        time = 0.0 + step * h
+    return X
+
+
+def fit_person(obs, dts, drift, meas, pars, person, m0, A0, Lmat, Rchol, alpha=.2, beta=2.0, kappa=0.0, h=1 / 30):
+    """Body of fitModel's person loop, SR variant (R/modelTemplate.R:244-411).  Returns (-2LL, latentScores, predictedManifest)."""
+    n = len(m0)
+    if n + kappa == 0:
+        kappa -= 1
+    c = alpha ** 2 * (n + kappa)
+    wm, wc = getMeanWeights(n, alpha, beta, kappa), getCovWeights(n, alpha, beta, kappa)
+    W = getWMatrix(wm, wc)
+    m, A = m0.astype(float).copy(), A0.astype(float).copy()
+    m2ll, tsum = 0.0, 0.0
+    lat, pred = [], []
+    for tp in range(len(dts)):
+        tsum += dts[tp]
+        ob = obs[tp]
+        nm = np.flatnonzero(np.isfinite(ob))
+        m_ = m.copy()
+        X = getSigmaPoints(m_, A, c)
+        if abs(dts[tp]) > 0:
+            X = integrate_const_rk4(X, dts[tp], h, lambda Z, t: rhs(Z, t, drift, pars, person, wm, wc, c, Lmat))
+            m_ = X[:, 0].copy()
+            A = np.tril(getAFromSigmaPoints(X, wm, c))
+        Y = np.column_stack([meas(X[:, i], pars, person, tsum) for i in range(X.shape[1])])
+        mu = Y @ wm
+        pred.append(mu)
+        if len(nm) > 0:
+            srS = predictSquareRootOfS(Y[nm], mu[nm], Rchol[np.ix_(nm, nm)], wc[0], wc[1])
+            C = X @ W @ Y[nm].T
+            si = np.linalg.inv(np.tril(srS))
+            K = C @ si.T @ si
+            m = m_ + K @ (ob - mu)[nm]
+            U = K @ srS
+            for co in range(U.shape[1]):
+                A = np.tril(cholupdate(A, U[:, co], 1, "downdate"))
+            m2ll += m2ll_chol(len(nm), ob[nm], mu[nm], srS)
+        else:
+            m = m_
+        lat.append(m.copy())
+    return m2ll, np.array(lat), np.array(pred)

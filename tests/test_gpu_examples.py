@@ -101,3 +101,29 @@ def test_nonlinear_measurement_reproduces_quirk_q3():
                                  integrateFunction="rk4", eps=np.array([1e-6]), srUpdate=False)})
     fit2 = _compare(m2)
     assert np.max(np.abs(fit["m2LL"] - fit2["m2LL"]) / np.abs(fit["m2LL"])) > 1e-6
+
+
+def test_time_conventions_and_operator_surface():
+    """Drift sees the interval-LOCAL time (integration restarts at 0 for every interval, R/modelTemplate.R:317-318),
+    the measurement equation the ABSOLUTE time (timeSum, :353-355); also exercises matrix containers, whole-vector
+    statements mixed with element statements, % and unary minus."""
+    kw = dict(
+        dataset=_data(6, 18, 2, 5, dt=0.7, scale=1.0, offset=0.5),
+        latentEquations="dx = DRIFT*x + CINT;\ndx(1) = dx(1) - 0.1*x(1)*x(1)*x(1) + 0.3*t;\ndx = dx - 0.01*(x % x);",
+        manifestEquations="y = LAMBDA*x;\ny = y + MANIFESTMEANS;\ny(0) = y(0) + 0.2*sin(0.5*t);",
+        parameters={"DRIFT": np.array([["d11 = -0.5", "0.1"], ["d21 = 0.2", "d22 = -0.6"]], dtype=object),
+                    "CINT": np.array([["c1 = 0.3"], ["0.1"]], dtype=object),
+                    "LAMBDA": np.array([["1", "0"], ["l21 = 0.4", "1"]], dtype=object),
+                    "MANIFESTMEANS": np.array([["0.2"], ["mm2 = -0.1"]], dtype=object)},
+        L=np.array([["l1 = 0.5", "0"], ["l21x = 0.1", "l2 = 0.4"]], dtype=object),       # lower-triangular (not diagonal) diffusion
+        Rchol=np.array([["r1 = 0.6", "0"], ["r21 = 0.1", "r2 = 0.5"]], dtype=object),     # non-diagonal measurement root
+        A0=np.array([["0.8", "0"], ["a21 = 0.1", "0.7"]], dtype=object), m0=np.array([[1.0], [0.5]]),
+        integrateFunction="rk4", eps=np.array([1e-6]))
+    m = pd.newPsydiff(**kw)
+    assert "L_STRUCT = psy::L_FULL" in m["cppCode"] and "R_DIAG = false" in m["cppCode"]
+    _compare(m, extended=True)          # nonlinear drift: gradient against the 80-bit oracle (DESIGN.md §5)
+    # the same model under dopri5 and in the covariance variant
+    m["integrateFunction"] = "runge_kutta_dopri5"
+    _compare(m, grad=False)
+    m3 = pd.newPsydiff(**dict(kw, srUpdate=False))
+    _compare(m3, extended=True)
