@@ -37,6 +37,9 @@
 #ifndef PSY_MIN_BLOCKS
 #define PSY_MIN_BLOCKS 1
 #endif
+#ifndef PSY_RHS_SCALED
+#define PSY_RHS_SCALED 1
+#endif
 
 namespace psy {
 
@@ -70,7 +73,7 @@ struct Filter {
   struct UT { double sqrtc, wm0, wm1, wc0, wc1, kap; };
 
   // ---- RHS of the reduced sigma-point ODE (replaces odeintModel::operator() + getMMatrix) -------------------
-  static __device__ __forceinline__ void rhs(const double (&p)[F], const double (&m)[N], const double (&A)[TN],
+  static __device__ __forceinline__ void rhs_plain(const double (&p)[F], const double (&m)[N], const double (&A)[TN],
                                              double (&dm)[N], double (&dA)[TN], const double (&Q)[QLEN],
                                              const UT& ut, int person, double t) {
     // explicit inverse of the lower-triangular root (arma::inv(arma::trimatl(A)), R/modelTemplate.R:97)
@@ -185,6 +188,141 @@ struct Filter {
         for (int k = j + 1; k <= i; k++) acc += A[tri(i, k)] * Ph[tri(k, j)];
         dA[tri(i, j)] = acc;
       }
+  }
+
+  // Column-scaled form of the same RHS (default, -DPSY_RHS_SCALED=0 selects rhs_plain).  With A = Ã·D, D = diag(A_jj), Ã unit
+  // lower triangular and W = Ã⁻¹ (unit lower):  A⁻¹ = D⁻¹W,  G = D⁻¹G̃ with G̃ = W·[d_1..d_n],
+  //   M = D⁻¹ M̃ D⁻¹,  M̃_ij = kap (G̃_ij A_jj + A_ii G̃_ji) + (W LLᵀ Wᵀ)_ij,   Phi(M) = D⁻¹ Phi(M̃) D⁻¹,   dA = A Phi(M) = (Ã Phi(M̃)) D⁻¹.
+  // Every unit diagonal turns the first term of a dot product into the accumulator's seed, so the triangular inverse,
+  // G̃, the diffusion term and Ã·Phi are pure FMA chains: 72 fewer FP64 instructions per evaluation at n = 6 for the same
+  // numbers up to rounding.
+  static __device__ __forceinline__ void rhs_scaled(const double (&p)[F], const double (&m)[N], const double (&A)[TN],
+                                                    double (&dm)[N], double (&dA)[TN], const double (&Q)[QLEN],
+                                                    const UT& ut, int person, double t) {
+    double rd[N], At[TN], W[TN];   // At / W: strictly-lower entries are used, the unit diagonal is implied
+#pragma unroll
+    for (int i = 0; i < N; i++) rd[i] = rcp(A[tri(i, i)]);
+#pragma unroll
+    for (int j = 0; j < N; j++)
+#pragma unroll
+      for (int i = j + 1; i < N; i++) At[tri(i, j)] = A[tri(i, j)] * rd[j];
+#pragma unroll
+    for (int j = 0; j < N; j++)
+#pragma unroll
+      for (int i = j + 1; i < N; i++) {
+        double acc = -At[tri(i, j)];
+#pragma unroll
+        for (int k = j + 1; k < i; k++) acc = fma(-At[tri(i, k)], W[tri(k, j)], acc);
+        W[tri(i, j)] = acc;
+      }
+    // drift at the 2n+1 sigma points, one evaluation per column; G̃[:,j] = W d_j
+    Vec<N> xc, f0;
+#pragma unroll
+    for (int i = 0; i < N; i++) { xc.v[i] = m[i]; f0.v[i] = 0.0; }
+    Mdl::latentEquation(xc, f0, p, person, t);
+    double fs[N], G[N * N];
+#pragma unroll
+    for (int i = 0; i < N; i++) fs[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      Vec<N> xp, xm, fp, fm;
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        if (i >= j) {
+          xp.v[i] = fma(ut.sqrtc, A[tri(i, j)], m[i]);
+          xm.v[i] = fma(-ut.sqrtc, A[tri(i, j)], m[i]);
+        } else {
+          xp.v[i] = m[i];
+          xm.v[i] = m[i];
+        }
+        fp.v[i] = 0.0;
+        fm.v[i] = 0.0;
+      }
+      Mdl::latentEquation(xp, fp, p, person, t);
+      Mdl::latentEquation(xm, fm, p, person, t);
+      double d[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        d[i] = fp.v[i] - fm.v[i];
+        fs[i] += fp.v[i] + fm.v[i];
+      }
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        double acc = d[i];
+#pragma unroll
+        for (int k = 0; k < i; k++) acc = fma(W[tri(i, k)], d[k], acc);
+        G[i + j * N] = acc;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) dm[i] = ut.wm0 * f0.v[i] + ut.wm1 * fs[i];
+
+    // Phi(M̃): lower triangle with the halved diagonal
+    double Ph[TN], ka[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) ka[i] = ut.kap * A[tri(i, i)];
+    if constexpr (Mdl::L_STRUCT == L_DIAG) {
+      // W diag(q) Wᵀ:  Bq = W diag(q) (unit diagonal -> Bq_kk = q_k)
+      double Bq[TN];
+#pragma unroll
+      for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int k = 0; k < i; k++) Bq[tri(i, k)] = W[tri(i, k)] * Q[k];
+#pragma unroll
+      for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+          double acc = (i == j) ? Q[j] : Bq[tri(i, j)];
+#pragma unroll
+          for (int k = 0; k < j; k++) acc = fma(Bq[tri(i, k)], W[tri(j, k)], acc);
+          if (i == j) acc = fma(G[i + i * N], ka[i], 0.5 * acc);
+          else acc = fma(G[i + j * N], ka[j], fma(G[j + i * N], ka[i], acc));
+          Ph[tri(i, j)] = acc;
+        }
+    } else {
+      // general L: Z = W Q (Q = L Lᵀ symmetric, packed lower), then lower(Z Wᵀ)
+      double Z[N * N];
+#pragma unroll
+      for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+          double acc = (i >= j) ? Q[tri(i, j)] : Q[tri(j, i)];
+#pragma unroll
+          for (int k = 0; k < i; k++) acc = fma(W[tri(i, k)], (k >= j) ? Q[tri(k, j)] : Q[tri(j, k)], acc);
+          Z[i + j * N] = acc;
+        }
+#pragma unroll
+      for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+          double acc = Z[i + j * N];
+#pragma unroll
+          for (int k = 0; k < j; k++) acc = fma(Z[i + k * N], W[tri(j, k)], acc);
+          if (i == j) acc = fma(G[i + i * N], ka[i], 0.5 * acc);
+          else acc = fma(G[i + j * N], ka[j], fma(G[j + i * N], ka[i], acc));
+          Ph[tri(i, j)] = acc;
+        }
+    }
+    // dA = (Ã Phi(M̃)) D⁻¹
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+      for (int j = 0; j <= i; j++) {
+        double acc = Ph[tri(i, j)];
+#pragma unroll
+        for (int k = j; k < i; k++) acc = fma(At[tri(i, k)], Ph[tri(k, j)], acc);
+        dA[tri(i, j)] = acc * rd[j];
+      }
+  }
+
+  static __device__ __forceinline__ void rhs(const double (&p)[F], const double (&m)[N], const double (&A)[TN],
+                                             double (&dm)[N], double (&dA)[TN], const double (&Q)[QLEN],
+                                             const UT& ut, int person, double t) {
+#if PSY_RHS_SCALED
+    rhs_scaled(p, m, A, dm, dA, Q, ut, person, t);
+#else
+    rhs_plain(p, m, A, dm, dA, Q, ut, person, t);
+#endif
   }
 
   // ---- classical RK4, K fixed steps (Boost.odeint integrate_const<runge_kutta4>, rule T1) -------------------

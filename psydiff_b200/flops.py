@@ -9,34 +9,36 @@ from __future__ import annotations
 
 
 def rhs_flops(n: int, Ff: int, l_diag: bool = True) -> int:
+    """One evaluation of Filter::rhs_scaled (column-scaled form: unit-diagonal FMA chains)."""
     tn = n * (n + 1) // 2
-    f = n  # reciprocals of the diagonal
-    for j in range(n):          # explicit triangular inverse
+    off = n * (n - 1) // 2
+    f = n                        # reciprocals of the diagonal
+    f += off                     # A~ = A D^-1
+    for j in range(n):           # W = A~^-1 (unit lower): seeded FMA chains
         for i in range(j + 1, n):
-            f += 1 + 2 * (i - j - 1) + 1
-    f += (2 * n + 1) * Ff       # drift at every sigma point
-    f += 3 * tn                 # sigma points m ± sqrt(c) A_j
-    f += 3 * n * n              # d = fp - fm, fs += fp + fm
-    for j in range(n):          # G[:, j] = Ainv d
-        for i in range(n):
-            f += 1 + 2 * i
-    f += 3 * n                  # dm
+            f += 2 * (i - j - 1)
+    f += (2 * n + 1) * Ff        # drift at every sigma point
+    f += 4 * tn                  # sigma points m ± sqrt(c) A_j (two FMAs per element)
+    f += 3 * n * n               # d = fp - fm, fs += fp + fm
+    f += n * n * (n - 1)         # G~[:, j] = W d_j: i FMAs for row i, n columns
+    f += 3 * n                   # dm
+    f += n                       # kap * A_jj
     if l_diag:
-        f += tn                 # Bq
+        f += off                 # Bq = W diag(q)
         for i in range(n):
             for j in range(i + 1):
-                f += 1 + 2 * j
+                f += 2 * j
     else:
-        for i in range(n):      # Z = Ainv Q
+        for i in range(n):       # Z = W Q, then lower(Z W')
             for j in range(n):
-                f += 2 * (i + 1)
+                f += 2 * i
         for i in range(n):
             for j in range(i + 1):
-                f += 2 * (j + 1)
-    f += 3 * tn + n             # g, kap*g + acc, halved diagonal
-    for i in range(n):          # dA = A Phi
+                f += 2 * j
+    f += 3 * n + 4 * off         # fold kap (G~ D + D G~') into Phi, halve the diagonal
+    for i in range(n):           # dA = (A~ Phi) D^-1
         for j in range(i + 1):
-            f += 1 + 2 * (i - j)
+            f += 2 * (i - j) + 1
     return f
 
 
