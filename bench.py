@@ -249,7 +249,9 @@ def main():
     steps_of = np.array([flops.rk4_step_count(float(d), hstep) if d != 0 else 0 for d in udt])
     rk4_total_per_person_avg = float((steps_of * cnt).sum()) / N_local
     inst_per_person = n_inst / N_local
-    fl_inst = flops.kernel_flops(6, 6, C4_FF, C4_FH, rk4_total_per_person_avg, T, l_diag=True)
+    from psydiff_b200 import codegen
+    fl_inst = flops.kernel_flops(6, 6, C4_FF, C4_FH, rk4_total_per_person_avg, T, l_diag=True,
+                                 dep=codegen.drift_dependency(model["_spec"]))
     fl_survey = flops.survey_flops(6, 6, C4_FF, C4_FH, rk4_total_per_person_avg, T)
     k_ms = float(ks.mean())
     achieved_formula = fl_inst * n_inst / (k_ms * 1e-3) / 1e12

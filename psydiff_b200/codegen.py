@@ -89,6 +89,47 @@ def _structure(c):
     return diag, lower
 
 
+_MATH_OK = {"exp", "log", "sqrt", "pow", "sin", "cos", "tan", "tanh", "sinh", "cosh", "fabs", "abs", "log1p", "expm1", "atan",
+            "std", "t", "person"}
+
+
+def drift_dependency(spec: ModelSpec) -> List[int]:
+    """Sparsity of the drift's Jacobian, as far as it can be read off the equation text: mask[i] has bit r set if
+    dx_i MAY depend on x_r.  Conservative — anything that is not a plain `dx(i) = <expression in x(k), parameters, t>;`
+    statement (or `dx = MATRIX*x;` with structurally zero entries) makes every component depend on every state.
+    The kernel uses it to skip the sigma-point columns that cannot change a component: there f(x+) = f(x-) = f(x0)
+    bit for bit, so the difference is exactly 0 and the sum exactly 2 f(x0) in the reference as well."""
+    n = spec.nlatent
+    full = (1 << n) - 1
+    names = {c.name: c for c in spec.containers}
+    stmts = [st.strip() for st in spec.latentEquations.replace("\n", " ").split(";") if st.strip()]
+    mask = [None] * n
+    for st in stmts:
+        m = re.match(r"^dx\s*[\(\[]\s*(\d+)\s*[\)\]]\s*=(?!=)\s*(.+)$", st, flags=re.S)
+        if m:
+            i, expr = int(m.group(1)), m.group(2)
+            if i >= n or mask[i] is not None:
+                return [full] * n                       # out of range / assigned twice: give up
+            deps = 0
+            rest = re.sub(r"\bx\s*[\(\[]\s*(\d+)\s*[\)\]]", lambda q: f" @{q.group(1)} ", expr)
+            for k in re.findall(r"@(\d+)", rest):
+                if int(k) >= n:
+                    return [full] * n
+                deps |= 1 << int(k)
+            idents = set(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", re.sub(r"@\d+", " ", rest)))
+            idents = {w for w in idents if not re.fullmatch(r"[eE]", w)}       # exponent of a float literal
+            if any((w not in _MATH_OK) and not (w in names and names[w].kind == "double") for w in idents):
+                return [full] * n                       # x used whole, dx on the right, matrices, temporaries, ...
+            mask[i] = deps
+            continue
+        m = re.match(r"^dx\s*=(?!=)\s*([A-Za-z_][A-Za-z0-9_]*)\s*\*\s*x$", st)
+        if m and m.group(1) in names and names[m.group(1)].shape == (n, n) and all(v is None for v in mask) and len(stmts) == 1:
+            c = names[m.group(1)]
+            return [sum(1 << k for k in range(n) if c.slots[i, k] >= 0 or c.values[i, k] != 0.0) for i in range(n)]
+        return [full] * n
+    return [0 if v is None else v for v in mask]        # a component never assigned stays 0 (dx is zero-initialised)
+
+
 def emit_cuda(spec: ModelSpec) -> str:
     n, m, F = spec.nlatent, spec.nmanifest, spec.n_slots
     A0, Ll, Rl, m0 = (spec.container(k) for k in ("A0LogChol", "LLogChol", "RLogChol", "m0"))
@@ -112,7 +153,11 @@ def emit_cuda(spec: ModelSpec) -> str:
     src.append(f"  static constexpr int L_STRUCT = {'psy::L_DIAG' if l_diag else 'psy::L_FULL'};\n")
     src.append(f"  static constexpr bool R_DIAG = {'true' if r_diag else 'false'};\n")
     src.append(f"  static constexpr bool SR = {'true' if spec.srUpdate else 'false'};\n")
-    src.append(f"  static constexpr int STEPPER = {int(spec.stepper)};\n\n")
+    src.append(f"  static constexpr int STEPPER = {int(spec.stepper)};\n")
+    dep = drift_dependency(spec)
+    chain = " : ".join(f"i == {i} ? {hex(dep[i])}u" for i in range(n - 1)) + (" : " if n > 1 else "") + f"{hex(dep[n - 1])}u"
+    src.append("  // bit r of dep(i): drift component i may read x_r (Jacobian sparsity read off the equation text)\n")
+    src.append(f"  static __host__ __device__ constexpr unsigned dep(int i) {{ return {chain}; }}\n\n")
     # latentEquation (R/prepareModel.R:493-505)
     src.append("  static __device__ __forceinline__ void latentEquation(const psy::Vec<N>& x, psy::Vec<N>& dx,\n"
                "      const double (&psy_p_)[NFREE], const int person, const double t) {\n")

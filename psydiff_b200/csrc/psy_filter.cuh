@@ -215,7 +215,10 @@ struct Filter {
         for (int k = j + 1; k < i; k++) acc = fma(-At[tri(i, k)], W[tri(k, j)], acc);
         W[tri(i, j)] = acc;
       }
-    // drift at the 2n+1 sigma points, one evaluation per column; G̃[:,j] = W d_j
+    // drift at the 2n+1 sigma points, one evaluation per column; G̃[:,j] = W d_j.
+    // Column j moves x_j..x_{n-1} only (A is lower triangular).  A drift component that reads none of them
+    // (Mdl::dep, the Jacobian sparsity the code generator found) has f(x+) = f(x-) = f(x0) bit for bit: its difference
+    // is exactly 0 and its sum exactly 2 f0, so neither is evaluated and the zero never enters an FMA chain.
     Vec<N> xc, f0;
 #pragma unroll
     for (int i = 0; i < N; i++) { xc.v[i] = m[i]; f0.v[i] = 0.0; }
@@ -243,19 +246,29 @@ struct Filter {
       double d[N];
 #pragma unroll
       for (int i = 0; i < N; i++) {
-        d[i] = fp.v[i] - fm.v[i];
-        fs[i] += fp.v[i] + fm.v[i];
+        if ((Mdl::dep(i) >> j) != 0u) {
+          d[i] = fp.v[i] - fm.v[i];
+          fs[i] += fp.v[i] + fm.v[i];
+        } else {
+          d[i] = 0.0;
+        }
       }
 #pragma unroll
       for (int i = 0; i < N; i++) {
         double acc = d[i];
 #pragma unroll
-        for (int k = 0; k < i; k++) acc = fma(W[tri(i, k)], d[k], acc);
+        for (int k = 0; k < i; k++)
+          if ((Mdl::dep(k) >> j) != 0u) acc = fma(W[tri(i, k)], d[k], acc);
         G[i + j * N] = acc;
       }
     }
 #pragma unroll
-    for (int i = 0; i < N; i++) dm[i] = ut.wm0 * f0.v[i] + ut.wm1 * fs[i];
+    for (int i = 0; i < N; i++) {
+      int unmoved = 0;  // columns that cannot change component i: each contributes 2 f0_i to the weighted mean
+#pragma unroll
+      for (int j = 0; j < N; j++) unmoved += ((Mdl::dep(i) >> j) != 0u) ? 0 : 1;
+      dm[i] = fma(ut.wm1, fs[i], (ut.wm0 + 2.0 * (double)unmoved * ut.wm1) * f0.v[i]);
+    }
 
     // Phi(M̃): lower triangle with the halved diagonal
     double Ph[TN], ka[N];

@@ -8,8 +8,12 @@
 from __future__ import annotations
 
 
-def rhs_flops(n: int, Ff: int, l_diag: bool = True) -> int:
-    """One evaluation of Filter::rhs_scaled (column-scaled form: unit-diagonal FMA chains)."""
+def rhs_flops(n: int, Ff: int, l_diag: bool = True, dep=None) -> int:
+    """One evaluation of Filter::rhs_scaled (column-scaled form: unit-diagonal FMA chains).  ``dep`` = the Jacobian
+    sparsity masks of codegen.drift_dependency (None = dense): unmoved (component, column) pairs cost nothing."""
+    if dep is None:
+        dep = [(1 << n) - 1] * n
+    moved = [[(dep[i] >> j) != 0 for j in range(n)] for i in range(n)]   # moved[i][j]: column j can change component i
     tn = n * (n + 1) // 2
     off = n * (n - 1) // 2
     f = n                        # reciprocals of the diagonal
@@ -19,8 +23,8 @@ def rhs_flops(n: int, Ff: int, l_diag: bool = True) -> int:
             f += 2 * (i - j - 1)
     f += (2 * n + 1) * Ff        # drift at every sigma point
     f += 4 * tn                  # sigma points m ± sqrt(c) A_j (two FMAs per element)
-    f += 3 * n * n               # d = fp - fm, fs += fp + fm
-    f += n * n * (n - 1)         # G~[:, j] = W d_j: i FMAs for row i, n columns
+    f += 3 * sum(moved[i][j] for i in range(n) for j in range(n))              # d = fp - fm, fs += fp + fm
+    f += 2 * sum(moved[k][j] for j in range(n) for i in range(n) for k in range(i))   # G~[:, j] = W d_j
     f += 3 * n                   # dm
     f += n                       # kap * A_jj
     if l_diag:
@@ -42,9 +46,9 @@ def rhs_flops(n: int, Ff: int, l_diag: bool = True) -> int:
     return f
 
 
-def step_flops(n: int, Ff: int, l_diag: bool = True) -> int:
+def step_flops(n: int, Ff: int, l_diag: bool = True, dep=None) -> int:
     ns = n + n * (n + 1) // 2
-    return 4 * rhs_flops(n, Ff, l_diag) + 4 * 4 * ns
+    return 4 * rhs_flops(n, Ff, l_diag, dep) + 4 * 4 * ns
 
 
 def update_flops(n: int, m: int, Fh: int) -> int:
@@ -73,9 +77,9 @@ def update_flops(n: int, m: int, Fh: int) -> int:
     return f + 4
 
 
-def kernel_flops(n, m, Ff, Fh, total_rk4_steps, timepoints, l_diag=True):
+def kernel_flops(n, m, Ff, Fh, total_rk4_steps, timepoints, l_diag=True, dep=None):
     """Executed flops of one filter instance that takes ``total_rk4_steps`` RK4 steps over ``timepoints`` time points."""
-    return total_rk4_steps * step_flops(n, Ff, l_diag) + timepoints * update_flops(n, m, Fh)
+    return total_rk4_steps * step_flops(n, Ff, l_diag, dep) + timepoints * update_flops(n, m, Fh)
 
 
 def survey_flops(n, m, Ff, Fh, total_rk4_steps, timepoints):

@@ -212,3 +212,28 @@ def test_exported_primitives_match_oracle_primitives():
     R = np.zeros((3, 3), order="F")
     L.psy_qr(7, 3, _lib.dptr(X), _lib.dptr(R))
     assert np.allclose(R.T @ R, X.T @ X)
+
+
+def test_drift_jacobian_sparsity_is_conservative():
+    """codegen.drift_dependency: exact for plain element statements, all-ones for anything it cannot read."""
+    full2 = [0b11, 0b11]
+    m = pd.newPsydiff(**synth.config_c4(N=2, T=3))
+    assert codegen.drift_dependency(m["_spec"]) == [0b10, 0b10111, 0b1000, 0b11101, 0b100000, 0b110101]
+    assert "dep(int i)" in m["cppCode"]
+    base = synth.config_c1(N=2, T=3)
+
+    def dep(latent, **kw):
+        return codegen.drift_dependency(pd.newPsydiff(**dict(base, latentEquations=latent, **kw))["_spec"])
+    assert dep("dx = DRIFT*x;") == full2                                   # every DRIFT entry is a free parameter
+    fixed = {"DRIFT": np.array([["a = -0.3", "0"], ["b = 0.2", "c = -0.5"]], dtype=object), "LAMBDA": base["parameters"]["LAMBDA"],
+             "MANIFESTMEANS": base["parameters"]["MANIFESTMEANS"]}
+    assert dep("dx = DRIFT*x;", parameters=fixed) == [0b01, 0b11]           # structural zero in DRIFT[0,1]
+    sc = dict(base["parameters"], a=-0.3, b=0.2)
+    assert dep("dx(0) = a*x(0);\n dx[1] = b*x[0] - 0.5*x[1]*exp(-x(0)*x(0)) + 2.5e-1*t;", parameters=sc) == [0b01, 0b11]
+    assert dep("dx(1) = a*x(1);", parameters=sc) == [0, 0b10]               # dx(0) never assigned: stays zero
+    # not understood -> everything depends on everything
+    assert dep("double tmp = x(0)*x(1); dx(0) = tmp; dx(1) = a*x(1);", parameters=sc) == full2
+    assert dep("dx(0) = a*x(0); dx(0) = dx(0) + x(1); dx(1) = b;", parameters=sc) == full2
+    assert dep("dx = DRIFT*x; dx(0) = dx(0) + a;", parameters=sc) == full2
+    assert dep("dx(0) = arma::accu(x); dx(1) = a*x(1);", parameters=sc) == full2
+    assert dep("dx(0) = DRIFT(0,0)*x(0); dx(1) = a*x(1);", parameters=sc) == full2   # matrix element access: not analysed
