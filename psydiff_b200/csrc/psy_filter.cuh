@@ -569,7 +569,7 @@ struct Filter {
                                               const UT& ut, double (&Z)[N][M], double (&w)[M], double& dist, double& ld) {
     double rS[M];
 #pragma unroll
-    for (int a = 0; a < M; a++) rS[a] = 1.0 / S[tri(a, a)];
+    for (int a = 0; a < M; a++) rS[a] = rcp(S[tri(a, a)]);
     dist = 0.0;
     ld = 0.0;
 #pragma unroll
@@ -611,14 +611,16 @@ struct Filter {
 #pragma unroll
     for (int i = 0; i < TM; i++) S[i] = 0.0;
     const double sw = sqrt(ut.wc1);
-    auto rotate_in = [&](double (&tr)[M]) {
+    // first: index of the row's first possibly non-zero entry (rotations before it would be identities)
+    auto rotate_in = [&](double (&tr)[M], int first) {
 #pragma unroll
       for (int k = 0; k < M; k++) {
+        if (k < first) continue;
         const double a = S[tri(k, k)], b = tr[k];
         const double r = sqrt(a * a + b * b);
         double c = 1.0, s = 0.0;
         if (r != 0.0) {
-          const double ri = 1.0 / r;
+          const double ri = rcp(r);
           c = a * ri;
           s = b * ri;
         }
@@ -635,18 +637,18 @@ struct Filter {
       double tr[M];
 #pragma unroll
       for (int a = 0; a < M; a++) tr[a] = z.miss[a] ? 0.0 : sw * (z.Y0.v[a] - z.mu[a]);
-      rotate_in(tr);
+      rotate_in(tr, 0);
 #pragma unroll
       for (int j = 0; j < N; j++) {
 #pragma unroll
         for (int a = 0; a < M; a++) tr[a] = z.miss[a] ? 0.0 : sw * (z.Yp[j].v[a] - z.mu[a]);
-        rotate_in(tr);
+        rotate_in(tr, 0);
       }
 #pragma unroll
       for (int j = 0; j < N; j++) {
 #pragma unroll
         for (int a = 0; a < M; a++) tr[a] = z.miss[a] ? 0.0 : sw * (z.Ym[j].v[a] - z.mu[a]);
-        rotate_in(tr);
+        rotate_in(tr, 0);
       }
       // columns of Rchol = logChol2Chol(RLogChol) (R/modelTemplate.R:277-278), masked
       double Rc[M * M];
@@ -657,11 +659,12 @@ struct Filter {
 #pragma unroll
           for (int a = 0; a < M; a++) tr[a] = 0.0;
           tr[b] = z.miss[b] ? 1.0 : Rc[b + b * M];
+          rotate_in(tr, b);
         } else {
 #pragma unroll
           for (int a = 0; a < M; a++) tr[a] = (z.miss[a] || z.miss[b]) ? ((a == b) ? 1.0 : 0.0) : Rc[a + b * M];
+          rotate_in(tr, 0);
         }
-        rotate_in(tr);
       }
     }
     // rank-1 up/down-date with column 0, weight |wc0| applied as v^(1/4) — reference quirk Q3, reproduced
@@ -676,9 +679,9 @@ struct Filter {
       for (int k = 0; k < M; k++) {
         const double lkk = S[tri(k, k)];
         const double r = sqrt(lkk * lkk + dir * x[k] * x[k]);
-        const double il = 1.0 / lkk;
+        const double il = rcp(lkk);
         const double c = r * il, s = x[k] * il;
-        const double ic = 1.0 / c;
+        const double ic = lkk * rcp(r);
         S[tri(k, k)] = r;
 #pragma unroll
         for (int i = k + 1; i < M; i++) {
@@ -708,9 +711,9 @@ struct Filter {
       for (int k = 0; k < N; k++) {
         const double lkk = A[tri(k, k)];
         const double r = sqrt(lkk * lkk - x[k] * x[k]);
-        const double il = 1.0 / lkk;
+        const double il = rcp(lkk);
         const double c = r * il, s = x[k] * il;
-        const double ic = 1.0 / c;
+        const double ic = lkk * rcp(r);
         A[tri(k, k)] = r;
 #pragma unroll
         for (int i = k + 1; i < N; i++) {
@@ -751,7 +754,7 @@ struct Filter {
       for (int k = 0; k < j; k++) d -= S[tri(j, k)] * S[tri(j, k)];
       d = sqrt(d);
       S[tri(j, j)] = d;
-      const double id = 1.0 / d;
+      const double id = rcp(d);
 #pragma unroll
       for (int i = j + 1; i < M; i++) {
         double a = S[tri(i, j)];
@@ -875,7 +878,7 @@ struct Filter {
           for (int k = 0; k < j; k++) d -= A[tri(j, k)] * A[tri(j, k)];
           d = sqrt(d);
           A[tri(j, j)] = d;
-          const double id = 1.0 / d;
+          const double id = rcp(d);
 #pragma unroll
           for (int i = j + 1; i < N; i++) {
             double a = P[tri(i, j)];
