@@ -1,13 +1,13 @@
 // psy_filter.cuh — K1, the fused per-instance SR-UKF filter kernel (hand-written FP64 CUDA for sm_100a).
 //
 // One CUDA thread owns one filter instance = (person, finite-difference perturbation) and carries it through
-// ALL of that person's time points: sigma points, the sigma-point matrix ODE (Särkkä 2007 eq. 34) under RK4,
-// the square-root measurement update and the -2LL accumulation never leave registers.  This replaces, for the
+// ALL of that person's time points: sigma points, the sigma-point matrix ODE (Särkkä 2007 eq. 34) under RK4 or adaptive
+// Dormand-Prince, the square-root (or covariance) measurement update and the -2LL accumulation never leave registers.  This replaces, for the
 // whole person x time loop, the reference's
 //   fitModel                         R/modelTemplate.R:165-420  (SR variant)
 //   odeintModel::operator()          R/modelTemplate.R:138-163
 //   getMMatrix / computeL            R/modelTemplate.R:77-135
-//   integrate_const<runge_kutta4>    call sites R/modelTemplate.R:327-329 (Boost.odeint)
+//   integrate_const<runge_kutta4>    call sites R/modelTemplate.R:327-329 (Boost.odeint); integrate() = dopri5 :331-333
 //   getSigmaPoints_C, getAFromSigmaPoints_C, getPhi_C, predictMu_C, predictC_C, predictSquareRootOfS_C (qr_C,
 //   cholupdate_C), computeK_SR_C, updateM_C, computeIndividualM2LLChol_C, logChol2Chol_C
 //                                    inst/include/psydiffInternals.h:4-209
@@ -21,7 +21,9 @@
 //     M = kap·(G + Gᵀ) + A⁻¹ L Lᵀ A⁻ᵀ,   G = A⁻¹ D,  D_j = f(m + sqrt(c)A_j) − f(m − sqrt(c)A_j),  kap = wc1·sqrt(c).
 // This is algebraically identical to getMMatrix's Σ wc_i (x_i − m_x)(f_i − m_f)ᵀ + transpose (the i = 0 term
 // vanishes because x_0 = m_x) and differs from the reference only by rounding (parity gate 1e-9 relative).
-// It is what lets one instance fit a thread's register file for n <= 6.
+// It is what lets one instance fit a thread's register file for n <= 6.  The RHS is evaluated in column-scaled form
+// (rhs_scaled: A = Ã·diag(A_jj), unit-lower Ã — pure FMA chains) and skips the sigma-point columns that cannot move a
+// drift component (Jacobian sparsity from the code generator, Mdl::dep).
 //
 // Missing manifests (NaN) are handled without dynamic indexing: a missing variable's deviations are zeroed and
 // its row/column of Rchol replaced by the unit vector, which makes srS block-diagonal with a unit entry there,
