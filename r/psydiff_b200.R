@@ -1,0 +1,55 @@
+# psydiff_b200.R — R side of the drop-in: same function names and return values as the reference
+# (compileModel R/prepareModel.R:553-562; fitModel / getGradients / getGradient R/modelTemplate.R:165-166, 853-854, 932-933;
+# getGradientsParallel R/prepareModel.R:608-616).  newPsydiff is unchanged except that model$cppCode is produced by the
+# CUDA code generator (a port of psydiff_b200/codegen.py) instead of modelTemplate().
+
+.psy_stepper <- function(f) switch(f, "rk4" = 0L, "runge_kutta_dopri5" = 1L, 2L)
+.psy_direction <- function(d) {
+  k <- match(d, c("central", "left", "right"))
+  if (is.na(k)) stop("Unknown direction argument. Possible are central, left and right")
+  k - 1L
+}
+.psy_settings <- function(m) list(c(m$alpha, m$beta, m$kappa), .psy_stepper(m$integrateFunction), as.numeric(m$timeStep),
+                                  isTRUE(m$srUpdate) || is.null(m$srUpdate))
+
+compileModel <- function(psydiffModel) {
+  pt <- psydiffModel$pars$parameterTable
+  persons <- unique(psydiffModel$data$person)
+  labs <- unique(pt$label)                                   # theta, first-appearance order
+  nfree <- nrow(pt) / length(persons)
+  tidx <- as.integer(match(pt$label, labs) - 1L)             # person-major, slot-minor: exactly psy_set_slots' layout
+  off <- c(0, cumsum(rle(as.vector(psydiffModel$data$person))$lengths))
+  psydiffModel$handle <- .Call("R_psy_compile", psydiffModel$cppCode, system.file("include", package = "psydiff"),
+                               tools::R_user_dir("psydiff", "cache"), psydiffModel$nlatent, psydiffModel$nmanifest, nfree,
+                               psydiffModel$data$observations, as.numeric(psydiffModel$data$dt), as.numeric(off),
+                               as.integer(persons), length(labs), tidx)
+  assign("fitModel", function(psydiffModel, skipUpdate = FALSE) {
+    s <- .psy_settings(psydiffModel)
+    out <- .Call("R_psy_fit", psydiffModel$handle, s[[1]], s[[2]], s[[3]], s[[4]], getParameterValues(psydiffModel), skipUpdate,
+                 length(unique(psydiffModel$data$person)), nrow(psydiffModel$data$observations), psydiffModel$nlatent,
+                 psydiffModel$nmanifest)
+    psydiffModel$pars$parameterTable$changed <- FALSE       # the reference clears the flags by reference (R/modelTemplate.R:410)
+    out
+  }, envir = globalenv())
+  assign("getGradients", function(psydiffModel) {
+    s <- .psy_settings(psydiffModel)
+    theta <- getParameterValues(psydiffModel)
+    g <- .Call("R_psy_gradients", psydiffModel$handle, s[[1]], s[[2]], s[[3]], s[[4]], theta, as.numeric(psydiffModel$eps),
+               .psy_direction(psydiffModel$direction))
+    names(g) <- names(theta)
+    g
+  }, envir = globalenv())
+  assign("getGradient", function(psydiffModel, currentParameterValues, par) {
+    s <- .psy_settings(psydiffModel)
+    g <- .Call("R_psy_gradient", psydiffModel$handle, s[[1]], s[[2]], s[[3]], s[[4]], currentParameterValues, as.integer(par),
+               as.numeric(psydiffModel$eps), .psy_direction(psydiffModel$direction))
+    names(g) <- names(currentParameterValues)[par + 1]
+    g
+  }, envir = globalenv())
+  invisible(psydiffModel)
+}
+
+# the PSOCK cluster of the reference is not needed: the whole parameter sweep is one batched launch
+compileParallelGradients <- function(psydiffModel, nCores) { psydiffModel$cl <- list(nCores = nCores); psydiffModel }
+stopParallelGradients <- function(psydiffModel) invisible(NULL)
+getGradientsParallel <- function(psydiffModel) getGradients(psydiffModel)

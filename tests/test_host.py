@@ -237,3 +237,13 @@ def test_drift_jacobian_sparsity_is_conservative():
     assert dep("dx = DRIFT*x; dx(0) = dx(0) + a;", parameters=sc) == full2
     assert dep("dx(0) = arma::accu(x); dx(1) = a*x(1);", parameters=sc) == full2
     assert dep("dx(0) = DRIFT(0,0)*x(0); dx(1) = a*x(1);", parameters=sc) == full2   # matrix element access: not analysed
+
+
+def test_r_shim_only_uses_declared_abi():
+    """r/psydiff_b200_shim.c (compiled by an R maintainer, not here): every psy_* it calls is declared in the header."""
+    hdr = open(os.path.join(ROOT, "include", "psydiff_b200.h")).read()
+    declared = set(re.findall(r"\b(psy_[A-Za-z0-9_]+)\s*\(", hdr)) | {"psy_model"}
+    shim = open(os.path.join(ROOT, "r", "psydiff_b200_shim.c")).read()
+    used = set(re.findall(r"\b(psy_[A-Za-z0-9_]+)\b", shim))
+    assert used - declared == set(), used - declared
+    assert {"psy_model_compile", "psy_model_create", "psy_upload", "psy_set_slots", "psy_fit", "psy_gradients", "psy_gradient"} <= used
