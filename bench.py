@@ -36,6 +36,7 @@ C4_FF, C4_FH = 39, 0   # flops of one drift / measurement evaluation of the C4 e
 # launch (profiles/r01d_psy_filter_kernel_c4_ncu_full_raw.csv: 28.22 Mflop/instance vs 31.08 from the formula) say the
 # compiled kernel executes 9 % fewer (constant folding, hoisted products).  roofline.achieved uses the ncu-calibrated count.
 C4_NCU_CALIBRATION = 0.908
+NCU_DRAM_BYTES_PER_PERSON = (28.271360e6 + 0.856832e6) / 4096   # same capture: DRAM traffic of one launch per person
 
 
 def parse():
@@ -276,7 +277,10 @@ def main():
         "clocks": clocks,
         "roofline": {
             "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
-            "traffic": None, "kernel": "psy_filter_kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
+            # ncu --set full of the 4096-person launch (profiles/r01d_*): dram read 28.27 MB + write 0.86 MB; linear in persons
+            "traffic": NCU_DRAM_BYTES_PER_PERSON * N_local,
+            "traffic_unit": "bytes/launch (ncu dram__bytes_read+write of the 4096-person capture, scaled by persons)",
+            "hbm_staging_gbs": (obs_host.nbytes + dtv.nbytes + 8 * n_inst) / (k_ms * 1e-3) / 1e9, "kernel": "psy_filter_kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
             "flops_per_instance": fl_inst * C4_NCU_CALIBRATION, "flops_per_instance_loop_count": fl_inst,
             "achieved_loop_count": achieved_formula, "ncu_calibration": C4_NCU_CALIBRATION,
             "flops_per_instance_survey_formula": fl_survey,
