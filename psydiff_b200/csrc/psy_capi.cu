@@ -248,7 +248,7 @@ __global__ void psy_reduce_final(const int* __restrict__ big_list, int n_big, co
   const int th = big_list[q];
   double a[5] = {0, 0, 0, 0, 0};
   for (int c = theta_chunk_off[th]; c < theta_chunk_off[th + 1]; c++)
-    for (int q = 0; q < 5; q++) a[q] += chunk_part[(size_t)c * 5 + q];
+    for (int v = 0; v < 5; v++) a[v] += chunk_part[(size_t)c * 5 + v];
   if (th == P) {
     partial[0] = a[0];
     partial[1] = a[1];
