@@ -33,9 +33,9 @@ METRIC = "SR-UKF person-timesteps/sec (-2LL + FD gradient, FP64)"
 UNIT = "person-timesteps/s"
 C4_FF, C4_FH = 39, 0   # flops of one drift / measurement evaluation of the C4 equations (counted from the model source)
 # flops.kernel_flops() walks the kernel's loop nests; ncu's DADD + DMUL + 2*DFMA thread-instruction counters for the same
-# launch (profiles/r01d_psy_filter_kernel_c4_ncu_full_raw.csv: 28.22 Mflop/instance vs 31.08 from the formula) say the
+# launch (profiles/r01e_final_kernel_ncu_counters.csv: 28.12 Mflop/instance vs 31.08 from the formula) say the
 # compiled kernel executes 9 % fewer (constant folding, hoisted products).  roofline.achieved uses the ncu-calibrated count.
-C4_NCU_CALIBRATION = 0.908
+C4_NCU_CALIBRATION = 0.905
 NCU_DRAM_BYTES_PER_PERSON = (28.271360e6 + 0.856832e6) / 4096   # same capture: DRAM traffic of one launch per person
 
 
