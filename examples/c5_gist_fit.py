@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--lambda", dest="lam", type=float, default=10.0)
     ap.add_argument("--outer", type=int, default=15)
     ap.add_argument("--bfgs-iters", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=8, help="line-search candidates evaluated per launch")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -44,7 +45,8 @@ def main():
     t0 = time.time()
     res = optim.GIST(model, start, lambda_=a.lam * npg * world / 2048, adaptiveLassoWeights={k: 1.0 for k in start},
                      regularizedParameters=gains, maxIter_out=a.outer, sig=.4, silent=True,
-                     fitTotal=pdist.fitTotalSharded, gradients=pdist.getGradientsSharded)
+                     fitTotal=pdist.fitTotalSharded, gradients=pdist.getGradientsSharded,
+                     batch=a.batch, fitTotalsMany=pdist.fitTotalsSharded)
     t_gist = time.time() - t0
     est = pd.getParameterValues(model)
     names = list(est)

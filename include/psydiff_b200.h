@@ -84,6 +84,12 @@ int psy_set_slots(psy_model* mdl, int n_theta, const int* theta_index);
 int psy_fit(psy_model* mdl, const double* theta, int skip_update, double* m2ll, double* latent_scores,
             double* predicted_manifest);
 
+/* fitModel for several parameter vectors in one launch (thetas: n_sets x P row-major): totals[k] = Σ_p -2LL over the persons
+ * with a finite value, nonfinite[k] = how many persons failed.  What a caller that evaluates psydiffFitInternal
+ * (R/optimWrapper.R:146-157) at several candidate points — GIST's inner line search (R/GIST.R:121-190), bestOfN
+ * (R/bestOfN.R:23-38) — can use instead of n_sets sequential fitModel calls. */
+int psy_fit_many(psy_model* mdl, const double* thetas, int n_sets, int skip_update, double* totals, double* nonfinite);
+
 /* getGradients / getGradientsParallel (R/modelTemplate.R:852-930, R/prepareModel.R:608-616): the whole finite-
  * difference sweep as one batched launch per eps level.  grad[P] (NaN where both eps[] fallbacks fail,
  * R/modelTemplate.R:885-898); m2ll_total (may be NULL) receives Σ -2LL at theta. */

@@ -39,6 +39,7 @@ SIGNATURES = {
     "psy_upload": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, c_double_p, c_double_p, c_int64_p, c_int_p]),
     "psy_set_slots": (C.c_int, [C.c_void_p, C.c_int, c_int_p]),
     "psy_fit": (C.c_int, [C.c_void_p, c_double_p, C.c_int, c_double_p, c_double_p, c_double_p]),
+    "psy_fit_many": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p]),
     "psy_gradients": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p]),
     "psy_gradient": (C.c_int, [C.c_void_p, c_double_p, C.c_int, c_double_p, C.c_int, C.c_int, c_double_p]),
     "psy_partial_len": (C.c_int64, [C.c_void_p]),

@@ -358,6 +358,7 @@ int launch_filter(psy_model* M, const PsyInst* d_list, const int* d_out_idx, int
   L.wc1 = L.wm1;
   L.n_inst = (int)count;
   L.skip_update = skip_update;
+  L.n_theta = M->P;
   const unsigned block = (unsigned)M->block;
   const unsigned grid = (unsigned)((count + block - 1) / block);
   void* args[] = {&L};
@@ -675,6 +676,39 @@ int psy_fit(psy_model* M, const double* theta, int skip_update, double* m2ll, do
     psy_to_colmajor<<<(unsigned)((tot + 255) / 256), 256>>>(dp, dp + tot, M->rows, M->m);
     g_launches++;
     CU_TRY(cudaMemcpy(pred_cm, dp + tot, sizeof(double) * tot, cudaMemcpyDeviceToHost));
+  }
+  return PSY_OK;
+}
+
+// Several parameter vectors in ONE launch: N x n_sets unperturbed instances (a line search's candidate steps, random
+// restarts, ...).  totals[k] = Σ_p -2LL at thetas[k*P ..], nonfinite[k] = number of persons whose -2LL is not finite.
+// Person sums are formed on the host in person order (deterministic).
+int psy_fit_many(psy_model* M, const double* thetas, int n_sets, int skip_update, double* totals, double* nonfinite) {
+  if (!M || !thetas || n_sets < 1 || !totals || !nonfinite) return fail(PSY_ERR_ARG, "psy_fit_many: bad arguments");
+  if (!M->d_tidx.p) return fail(PSY_ERR_STATE, "psy_fit_many: call psy_upload and psy_set_slots first");
+  const int N = M->N, P = M->P;
+  const int64_t cnt = (int64_t)N * n_sets;
+  if (cnt > 2147483000LL) return fail(PSY_ERR_ARG, "psy_fit_many: too many instances");
+  int rc;
+  if ((rc = M->d_theta.alloc((size_t)std::max(P, 1) * n_sets))) return rc;
+  if (P > 0) CU_TRY(cudaMemcpy(M->d_theta.p, thetas, sizeof(double) * P * n_sets, cudaMemcpyHostToDevice));
+  if ((rc = M->d_f.alloc((size_t)std::max<int64_t>(cnt, M->n_inst)))) return rc;
+  // set-major blocks of persons: lanes of a warp share their person's neighbours' dt pattern as in psy_fit
+  std::vector<PsyInst> list((size_t)cnt);
+  for (int k = 0; k < n_sets; k++)
+    for (int p = 0; p < N; p++) list[(size_t)k * N + p] = PsyInst{p, -1 - k};
+  if ((rc = M->d_inst_sub.upload(list.data(), list.size()))) return rc;
+  if ((rc = launch_filter(M, M->d_inst_sub.p, nullptr, cnt, 0.0, skip_update, nullptr, nullptr))) return rc;
+  std::vector<double> f((size_t)cnt);
+  CU_TRY(cudaMemcpy(f.data(), M->d_f.p, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < n_sets; k++) {
+    double s = 0.0, bad = 0.0;
+    for (int p = 0; p < N; p++) {
+      const double v = f[(size_t)k * N + p];
+      if (std::isfinite(v)) s += v; else bad += 1.0;
+    }
+    totals[k] = s;
+    nonfinite[k] = bad;
   }
   return PSY_OK;
 }

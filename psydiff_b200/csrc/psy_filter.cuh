@@ -796,6 +796,7 @@ struct Filter {
     double p[F];
     {
       const int* ti = L.theta_index + (size_t)person * Mdl::NSLOT;
+      const double* th = L.theta + ((in.code < -1) ? (size_t)(-1 - in.code) * (size_t)L.n_theta : (size_t)0);
       const int pert = (in.code >= 0) ? (in.code >> 1) : -1;
       const double sh = (in.code & 1) ? L.eps : -L.eps;
 #pragma unroll
@@ -803,7 +804,7 @@ struct Filter {
 #pragma unroll
       for (int k = 0; k < Mdl::NSLOT; k++) {
         const int t = __ldg(ti + k);
-        double v = __ldg(L.theta + t);
+        double v = __ldg(th + t);
         if (t == pert) v += sh;
         p[k] = v;
       }
@@ -840,7 +841,7 @@ struct Filter {
     }
     const long long r0 = __ldg(L.row_off + person);
     const int T = (int)(__ldg(L.row_off + person + 1) - r0);
-    const bool base = (in.code < 0);
+    const bool base = (in.code == -1);
     // covariance variant state: P = A0 A0', R = Rchol Rchol' (R/modelTemplate.R:694-698)
     double P[Mdl::SR ? 1 : TN], RR[Mdl::SR ? 1 : TM];
     if constexpr (!Mdl::SR) {

@@ -138,3 +138,19 @@ def psydiffGradientsInternalSharded(pars, parsnames=None, model=None, group=None
     out = np.array([g[n] for n in names], dtype=float)
     out[np.isnan(out)] = 1.0
     return out
+
+
+def fitTotalsSharded(psydiffModel, parameterSets, group=None) -> np.ndarray:
+    """fitTotals over person shards: K totals (NaN where any person of any shard failed), one all-reduce of 2K doubles."""
+    import torch
+    import torch.distributed as dist
+    from .model import fitTotals
+    tot, bad = fitTotals(psydiffModel, parameterSets)
+    t = torch.tensor(np.concatenate([tot, bad]), dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    v = t.cpu().numpy()
+    K = len(tot)
+    out = v[:K].copy()
+    out[v[K:] > 0] = np.nan
+    return out

@@ -499,6 +499,22 @@ def fitModel(psydiffModel, skipUpdate: bool = False, states: bool = True):
     return {"latentScores": lat, "predictedManifest": pred, "m2LL": m2ll}
 
 
+def fitTotals(psydiffModel, parameterSets, skipUpdate: bool = False):
+    """Σ -2LL at several parameter vectors in ONE launch (not in the reference; it is what its callers that evaluate
+    psydiffFitInternal at many candidate points would use: GIST's line search, bestOfN).  ``parameterSets``: K x P array in
+    the order of getParameterValues(model), or a list of {label: value} dicts.  Returns (totals[K], nonfinite[K]); the
+    model's parameter table is not modified."""
+    h = _push_settings(psydiffModel)
+    pt = psydiffModel["pars"]["parameterTable"]
+    if len(parameterSets) and isinstance(parameterSets[0], dict):
+        parameterSets = [[ps[l] for l in pt.theta_labels] for ps in parameterSets]
+    th = np.ascontiguousarray(parameterSets, dtype=np.float64).reshape(-1, len(pt.theta_labels))
+    K = th.shape[0]
+    tot, bad = np.empty(K), np.empty(K)
+    _lib.check(_lib.lib().psy_fit_many(h.ptr, _lib.dptr(th), K, 1 if skipUpdate else 0, _lib.dptr(tot), _lib.dptr(bad)))
+    return tot, bad
+
+
 _DIRS = {"central": 0, "left": 1, "right": 2}
 
 

@@ -12,7 +12,7 @@ from typing import Dict, Optional, Sequence
 import numpy as np
 
 from ._lib import PsydiffError
-from .model import (clonePsydiffModel, fitModel, getGradients, getGradientsParallel, getParameterValues,
+from .model import (clonePsydiffModel, fitModel, fitTotals, getGradients, getGradientsParallel, getParameterValues,
                     setParameterValues)
 
 DOUBLE_XMAX = sys.float_info.max
@@ -252,11 +252,15 @@ def getSubgradients(theta: Dict[str, float], jacobian: Dict[str, float], regIndi
 def GIST(model, startingValues: Dict[str, float], lambda_, adaptiveLassoWeights: Dict[str, float], regularizedParameters,
          eta=1.5, sig=.2, initialStepsize=1.0, stepsizeMin=0.0, stepsizeMax=999999999.0,
          GISTLinesearchCriterion="monotone", GISTNonMonotoneNBack=5, maxIter_out=100, maxIter_in=100, break_outer=1e-8,
-         verbose=0, silent=False, rng: Optional[np.random.Generator] = None, fitTotal=None, gradients=None):
+         verbose=0, silent=False, rng: Optional[np.random.Generator] = None, fitTotal=None, gradients=None,
+         batch: int = 1, fitTotalsMany=None):
     """GIST (R/GIST.R:25-283; Gong et al. 2013): proximal-gradient lasso / adaptive lasso around fitModel + getGradients.
     ``rng`` drives the reference's random step-size reset (`runif(1) > .9`, R/GIST.R:88); ``rng=None`` disables it.
     ``fitTotal(model) -> Σ-2LL or NaN`` and ``gradients(model) -> dict`` replace fitModel / getGradients when persons are
-    sharded over GPUs (psydiff_b200.dist.fitTotalSharded / getGradientsSharded); every rank then runs the same loop."""
+    sharded over GPUs (psydiff_b200.dist.fitTotalSharded / getGradientsSharded); every rank then runs the same loop.
+    ``batch`` > 1 evaluates that many consecutive candidates of the inner line search (step sizes s, eta s, eta² s, ...) in
+    ONE launch (fitTotals, or ``fitTotalsMany(model, [dict, ...]) -> totals`` for shards) and then walks them in order, so
+    the accepted step and every returned value are exactly those of the sequential loop."""
     getGradients_ = gradients or getGradients
 
     def fit_at(values: Dict[str, float]):
@@ -300,34 +304,53 @@ def GIST(model, startingValues: Dict[str, float], lambda_, adaptiveLassoWeights:
             if stepsize < stepsizeMin or stepsize > stepsizeMax:
                 stepsize = initialStepsize
         par_kp1, m2LL_kp1, reg_kp1 = par_k, m2LL_k, reg_k
-        while k < maxIter_in:
-            u = vec(par_k) - vec(grad_k) / stepsize
+
+        def proximal(step):
+            u = vec(par_k) - vec(grad_k) / step
             new = {}
             for i, nme in enumerate(names):
                 if nme in regularizedParameters:
                     lam_i = lambda_ * adaptiveLassoWeights[nme]
-                    new[nme] = float(np.sign(u[i]) * max(0.0, abs(u[i]) - lam_i / stepsize))     # soft threshold
+                    new[nme] = float(np.sign(u[i]) * max(0.0, abs(u[i]) - lam_i / step))     # soft threshold
                 else:
                     new[nme] = float(u[i])
-            f = fit_at(new)
-            if f is None:
-                stepsize *= eta
-                k += 1
-                continue
-            par_kp1, m2LL_kp1 = new, f
-            reg_kp1 = f + getRegValue(lambda_, new, regularizedParameters, adaptiveLassoWeights)
-            d2 = float(np.sum((vec(par_k) - vec(new)) ** 2))
-            if GISTLinesearchCriterion == "monotone":
-                ok = reg_kp1 <= reg_k - (sig / 2) * stepsize * d2
-            elif GISTLinesearchCriterion == "non-monotone":
-                nback = max(1, k_out - GISTNonMonotoneNBack)
-                ok = reg_kp1 <= np.nanmax(regM2LL[nback - 1:k_out]) - (sig / 2) * stepsize * d2
+            return new
+
+        accepted = False
+        while k < maxIter_in and not accepted:
+            nb = max(1, min(int(batch), maxIter_in - k))
+            steps = [stepsize * eta ** i for i in range(nb)]
+            cands = [proximal(st) for st in steps]
+            if nb == 1:
+                fits = [fit_at(cands[0])]
             else:
-                raise PsydiffError("Unknown GISTLinesearchCriterion. Possible are monotone and non-monotone.")
-            if ok:
-                break
-            stepsize *= eta
-            k += 1
+                if fitTotalsMany is not None:
+                    tots = np.asarray(fitTotalsMany(model, cands), dtype=float)
+                else:
+                    tot, bad = fitTotals(model, cands)
+                    tots = np.where(bad > 0, np.nan, tot)
+                fits = [None if np.isnan(v) else float(v) for v in tots]
+            for st, new, f in zip(steps, cands, fits):
+                stepsize = st
+                if f is None:
+                    stepsize = st * eta
+                    k += 1
+                    continue
+                par_kp1, m2LL_kp1 = new, f
+                reg_kp1 = f + getRegValue(lambda_, new, regularizedParameters, adaptiveLassoWeights)
+                d2 = float(np.sum((vec(par_k) - vec(new)) ** 2))
+                if GISTLinesearchCriterion == "monotone":
+                    ok = reg_kp1 <= reg_k - (sig / 2) * stepsize * d2
+                elif GISTLinesearchCriterion == "non-monotone":
+                    nback = max(1, k_out - GISTNonMonotoneNBack)
+                    ok = reg_kp1 <= np.nanmax(regM2LL[nback - 1:k_out]) - (sig / 2) * stepsize * d2
+                else:
+                    raise PsydiffError("Unknown GISTLinesearchCriterion. Possible are monotone and non-monotone.")
+                if ok:
+                    accepted = True
+                    break
+                stepsize = st * eta
+                k += 1
         if k == maxIter_in and not silent:
             warnings.warn("Maximal number of inner iterations used by GIST. Consider increasing the number of inner iterations.")
         setParameterValues(model["pars"]["parameterTable"], par_kp1)

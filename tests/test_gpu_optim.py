@@ -68,3 +68,26 @@ def test_simulate_data_and_best_of_n():
     assert 0.3 < resid.std() < 1.2                       # Rchol = diag(sqrt(.5))
     best = optim.bestOfN(m, nstart=5, sd=.05, rng=np.random.default_rng(2))
     assert best is not None and set(best) == set(pd.getParameterValues(m))
+
+
+def test_fit_totals_many_sets_one_launch_and_batched_gist():
+    m = _model(N=40, T=20)
+    base = pd.getParameterValues(m)
+    sets = [dict(base), dict(base, drift_eta1=-0.6, mm_Y1=0.3), dict(base, drift_eta1=500.0)]       # the last one explodes
+    tot, bad = pd.fitTotals(m, sets)
+    assert pd.getParameterValues(m) == base                               # the model is not modified
+    for k in range(2):
+        pd.setParameterValues(m["pars"]["parameterTable"], sets[k])
+        assert tot[k] == pytest.approx(float(pd.fitModel(m)["m2LL"].sum()), rel=1e-13) and bad[k] == 0
+    assert bad[2] == 40
+    pd.setParameterValues(m["pars"]["parameterTable"], base)
+    # GIST with the inner line search evaluated 4 candidates per launch == the sequential loop
+    start = dict(base, drift_eta1_eta2=0.15)
+    w = {k: 1.0 for k in start}
+    kw = dict(lambda_=8.0, adaptiveLassoWeights=w, regularizedParameters=["drift_eta1_eta2"], maxIter_out=8, sig=.4, silent=True)
+    a = optim.GIST(pd.clonePsydiffModel(m), start, **kw)
+    b = optim.GIST(pd.clonePsydiffModel(m), start, batch=4, **kw)
+    ra, rb = a["regM2LL"][np.isfinite(a["regM2LL"])], b["regM2LL"][np.isfinite(b["regM2LL"])]
+    assert len(ra) == len(rb) and np.allclose(ra, rb, rtol=1e-11)
+    pa, pb = pd.getParameterValues(a["model"]), pd.getParameterValues(b["model"])
+    assert np.allclose(list(pa.values()), list(pb.values()), rtol=1e-9, atol=1e-12)
