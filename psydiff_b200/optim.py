@@ -390,18 +390,22 @@ def bestOfN(model, minVal=-5, maxVal=5, sd=.5, nstart=100, rng: Optional[np.rand
         raise PsydiffError("Length of maxVal does not correspond to the number of parameters in the model")
     if len(sd) != P:
         raise PsydiffError("Length of sd does not correspond to the number of parameters in the model")
-    work = clonePsydiffModel(model)
-    best, bestfit = None, np.inf
+    # draw all nstart candidates first (same sampling scheme as the reference), then evaluate them 32 per launch
+    cands = []
     for _ in range(nstart):
         cur = x.copy()
         for p in range(P):
             grid = np.linspace(minVal[p], maxVal[p], 1000)
             w = np.exp(-0.5 * ((grid - x[p]) / sd[p]) ** 2)
             cur[p] = rng.choice(grid, p=w / w.sum())
-        setParameterValues(work["pars"]["parameterTable"], cur, names)
-        f = float(np.sum(fitModel(work)["m2LL"]))
-        if np.isfinite(f) and f < bestfit:
-            bestfit, best = f, dict(zip(names, cur))
+        cands.append(cur)
+    best, bestfit = None, np.inf
+    for c0 in range(0, nstart, 32):
+        chunk = cands[c0:c0 + 32]
+        tot, bad = fitTotals(model, np.asarray(chunk))
+        for cur, f, b in zip(chunk, tot, bad):
+            if b == 0 and np.isfinite(f) and f < bestfit:
+                bestfit, best = float(f), dict(zip(names, cur))
     return best
 
 
