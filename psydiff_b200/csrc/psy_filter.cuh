@@ -198,10 +198,13 @@ struct Filter {
   // Every unit diagonal turns the first term of a dot product into the accumulator's seed, so the triangular inverse,
   // G̃, the diffusion term and Ã·Phi are pure FMA chains: 72 fewer FP64 instructions per evaluation at n = 6 for the same
   // numbers up to rounding.
+  // SCALE = false leaves out the final D⁻¹ (dA_ij = raw_ij · rd_j) and hands rd back: the RK4 driver folds it into its
+  // step coefficients (2n multiplies instead of n(n+1)/2).
+  template <bool SCALE>
   static __device__ __forceinline__ void rhs_scaled(const double (&p)[F], const double (&m)[N], const double (&A)[TN],
-                                                    double (&dm)[N], double (&dA)[TN], const double (&Q)[QLEN],
+                                                    double (&dm)[N], double (&dA)[TN], double (&rd)[N], const double (&Q)[QLEN],
                                                     const UT& ut, int person, double t) {
-    double rd[N], At[TN], W[TN];   // At / W: strictly-lower entries are used, the unit diagonal is implied
+    double At[TN], W[TN];   // At / W: strictly-lower entries are used, the unit diagonal is implied
 #pragma unroll
     for (int i = 0; i < N; i++) rd[i] = rcp(A[tri(i, i)]);
 #pragma unroll
@@ -225,9 +228,15 @@ struct Filter {
 #pragma unroll
     for (int i = 0; i < N; i++) { xc.v[i] = m[i]; f0.v[i] = 0.0; }
     Mdl::latentEquation(xc, f0, p, person, t);
-    double fs[N], G[N * N];
+    double G[N * N];
+    // weighted mean drift, accumulated by FMA: the columns that cannot move component i contribute 2 wm1 f0_i each
 #pragma unroll
-    for (int i = 0; i < N; i++) fs[i] = 0.0;
+    for (int i = 0; i < N; i++) {
+      int unmoved = 0;
+#pragma unroll
+      for (int j = 0; j < N; j++) unmoved += ((Mdl::dep(i) >> j) != 0u) ? 0 : 1;
+      dm[i] = (ut.wm0 + 2.0 * (double)unmoved * ut.wm1) * f0.v[i];
+    }
 #pragma unroll
     for (int j = 0; j < N; j++) {
       Vec<N> xp, xm, fp, fm;
@@ -250,7 +259,7 @@ struct Filter {
       for (int i = 0; i < N; i++) {
         if ((Mdl::dep(i) >> j) != 0u) {
           d[i] = fp.v[i] - fm.v[i];
-          fs[i] += fp.v[i] + fm.v[i];
+          dm[i] = fma(ut.wm1, fp.v[i] + fm.v[i], dm[i]);   // one add off the critical path, one FMA on the accumulation chain
         } else {
           d[i] = 0.0;
         }
@@ -263,13 +272,6 @@ struct Filter {
           if ((Mdl::dep(k) >> j) != 0u) acc = fma(W[tri(i, k)], d[k], acc);
         G[i + j * N] = acc;
       }
-    }
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-      int unmoved = 0;  // columns that cannot change component i: each contributes 2 f0_i to the weighted mean
-#pragma unroll
-      for (int j = 0; j < N; j++) unmoved += ((Mdl::dep(i) >> j) != 0u) ? 0 : 1;
-      dm[i] = fma(ut.wm1, fs[i], (ut.wm0 + 2.0 * (double)unmoved * ut.wm1) * f0.v[i]);
     }
 
     // Phi(M̃): lower triangle with the halved diagonal
@@ -326,7 +328,7 @@ struct Filter {
         double acc = Ph[tri(i, j)];
 #pragma unroll
         for (int k = j; k < i; k++) acc = fma(At[tri(i, k)], Ph[tri(k, j)], acc);
-        dA[tri(i, j)] = acc * rd[j];
+        dA[tri(i, j)] = SCALE ? acc * rd[j] : acc;
       }
   }
 
@@ -334,7 +336,8 @@ struct Filter {
                                              double (&dm)[N], double (&dA)[TN], const double (&Q)[QLEN],
                                              const UT& ut, int person, double t) {
 #if PSY_RHS_SCALED
-    rhs_scaled(p, m, A, dm, dA, Q, ut, person, t);
+    double rd[N];
+    rhs_scaled<true>(p, m, A, dm, dA, rd, Q, ut, person, t);
 #else
     rhs_plain(p, m, A, dm, dA, Q, ut, person, t);
 #endif
@@ -369,8 +372,15 @@ struct Filter {
         for (int st = 0; st < 4; st++) {
           double km[N], kA[TN];
           const double tc = (st == 0) ? t0 : ((st == 3) ? t0 + h : t0 + 0.5 * h);
-          rhs(p, m, A, km, kA, Q, ut, person, tc);
           const double b = (st == 0 || st == 3) ? h * (1.0 / 6.0) : h * (1.0 / 3.0);
+          double rdv[N];
+#if PSY_RHS_SCALED
+          rhs_scaled<false>(p, m, A, km, kA, rdv, Q, ut, person, tc);   // D⁻¹ is folded into the step coefficients below
+#else
+          rhs(p, m, A, km, kA, Q, ut, person, tc);
+#pragma unroll
+          for (int j = 0; j < N; j++) rdv[j] = 1.0;
+#endif
           // phased access: all loads first (they pipeline), then the arithmetic, then all stores
           double ta[N + TN], tx[N + TN];
 #pragma unroll
@@ -382,14 +392,25 @@ struct Filter {
 #pragma unroll
             for (int i = 0; i < N; i++) { ta[i] = fma(b, km[i], ta[i]); m[i] = fma(a, km[i], tx[i]); }
 #pragma unroll
-            for (int i = 0; i < TN; i++) { ta[N + i] = fma(b, kA[i], ta[N + i]); A[i] = fma(a, kA[i], tx[N + i]); }
+            for (int j = 0; j < N; j++) {
+              const double bj = b * rdv[j], aj = a * rdv[j];
+#pragma unroll
+              for (int i = j; i < N; i++) {
+                ta[N + tri(i, j)] = fma(bj, kA[tri(i, j)], ta[N + tri(i, j)]);
+                A[tri(i, j)] = fma(aj, kA[tri(i, j)], tx[N + tri(i, j)]);
+              }
+            }
 #pragma unroll
             for (int i = 0; i < N + TN; i++) sa[i * PSY_BLOCK] = ta[i];
           } else {
 #pragma unroll
             for (int i = 0; i < N; i++) m[i] = fma(b, km[i], ta[i]);
 #pragma unroll
-            for (int i = 0; i < TN; i++) A[i] = fma(b, kA[i], ta[N + i]);
+            for (int j = 0; j < N; j++) {
+              const double bj = b * rdv[j];
+#pragma unroll
+              for (int i = j; i < N; i++) A[tri(i, j)] = fma(bj, kA[tri(i, j)], ta[N + tri(i, j)]);
+            }
           }
         }
       }
@@ -406,13 +427,30 @@ struct Filter {
         for (int st = 0; st < 4; st++) {
           double km[N], kA[TN];
           const double tc = (st == 0) ? t0 : ((st == 3) ? t0 + h : t0 + 0.5 * h);
-          rhs(p, mt, At, km, kA, Q, ut, person, tc);
           const double b = (st == 0 || st == 3) ? h * (1.0 / 6.0) : h * (1.0 / 3.0);
           const double a = (st == 2) ? h : 0.5 * h;
+#if PSY_RHS_SCALED
+          // column scaling D⁻¹ of dA folded into the step coefficients
+          double rdv[N];
+          rhs_scaled<false>(p, mt, At, km, kA, rdv, Q, ut, person, tc);
+#pragma unroll
+          for (int i = 0; i < N; i++) { ma[i] += b * km[i]; mt[i] = m[i] + a * km[i]; }
+#pragma unroll
+          for (int j = 0; j < N; j++) {
+            const double bj = b * rdv[j], aj = a * rdv[j];
+#pragma unroll
+            for (int i = j; i < N; i++) {
+              Aa[tri(i, j)] = fma(bj, kA[tri(i, j)], Aa[tri(i, j)]);
+              At[tri(i, j)] = fma(aj, kA[tri(i, j)], A[tri(i, j)]);
+            }
+          }
+#else
+          rhs(p, mt, At, km, kA, Q, ut, person, tc);
 #pragma unroll
           for (int i = 0; i < N; i++) { ma[i] += b * km[i]; mt[i] = m[i] + a * km[i]; }
 #pragma unroll
           for (int i = 0; i < TN; i++) { Aa[i] += b * kA[i]; At[i] = A[i] + a * kA[i]; }
+#endif
         }
 #pragma unroll
         for (int i = 0; i < N; i++) m[i] = ma[i];
