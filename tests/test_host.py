@@ -247,3 +247,45 @@ def test_r_shim_only_uses_declared_abi():
     used = set(re.findall(r"\b(psy_[A-Za-z0-9_]+)\b", shim))
     assert used - declared == set(), used - declared
     assert {"psy_model_compile", "psy_model_create", "psy_upload", "psy_set_slots", "psy_fit", "psy_gradients", "psy_gradient"} <= used
+
+
+def _literal_parameter_table(slot_labels, persons, grouping, groupingvariables):
+    """R/prepareModel.R:471-476 + makeGroups :704-734, row by row, the slow way: replicate the slot rows per person, relabel
+    grouped parameters, then unique() in order of appearance (quirk Q6: first-appearance order)."""
+    rows = [[lab, p] for p in persons for lab in slot_labels]
+    if grouping:
+        for grp in [g for g in grouping.replace("\n", "").replace(" ", "").split(";") if g]:
+            par, var = grp.split("|")
+            for r in rows:
+                if r[0] == par:
+                    if var in ("person", "persons", "individual", "individuals"):
+                        r[0] = f"{par}_p{int(r[1])}"
+                    else:
+                        r[0] = f"{par}_p{int(groupingvariables[var][int(r[1]) - 1])}"
+    labels = []
+    for lab, _ in rows:
+        if lab not in labels:
+            labels.append(lab)
+    F = len(slot_labels)
+    idx = [[labels.index(rows[i * F + k][0]) for k in range(F)] for i in range(len(persons))]
+    return labels, idx
+
+
+def test_slot_map_equals_literal_parameter_table_on_random_groupings():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(2, 9), st.lists(st.sampled_from(["none", "person", "g1", "g2"]), min_size=11, max_size=11), st.integers(0, 10 ** 6))
+    def check(N, kinds, seed):
+        rng = np.random.default_rng(seed)
+        kw = synth.config_c1(N=N, T=2)
+        gv = {"g1": rng.integers(1, 4, size=N).astype(float), "g2": rng.integers(1, 3, size=N).astype(float)}
+        slot_labels = ["drift_eta1", "drift_eta1_eta2", "drift_eta2_eta1", "drift_eta2", "mm_Y1", "mm_Y2", "lnT0var_eta1",
+                       "T0var_eta2_eta1", "lnT0var_eta2", "lneta1_eta1", "lneta2_eta2"]
+        grouping = "".join(f"{lab} | {k};\n" for lab, k in zip(slot_labels, kinds) if k != "none") or None
+        m = pd.newPsydiff(**dict(kw, grouping=grouping, groupingvariables=gv if grouping else None))
+        pt = m["pars"]["parameterTable"]
+        labels, idx = _literal_parameter_table(slot_labels, list(range(1, N + 1)), grouping, gv)
+        assert pt.theta_labels == labels
+        assert pt.theta_index.tolist() == idx
+    check()
