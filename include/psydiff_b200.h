@@ -49,7 +49,8 @@ int psy_rk4_step_count(double t1, double h);
 /* ---- compileModel (R/prepareModel.R:553-562) ---------------------------------------------------------------
  * The reference writes model$cppCode to a temp file and hands it to Rcpp::sourceCpp (host g++).  Here the
  * generated CUDA translation unit (user drift + measurement statements spliced into the filter kernel template,
- * cf. R/prepareModel.R:479-512) is compiled for sm_100a with nvcc and cached by content hash.
+ * cf. R/prepareModel.R:479-512) is compiled for sm_100a and cached by content hash: with an `nvcc -cubin` subprocess by
+ * default, or in-process through NVRTC (dlopen'ed libnvrtc, no nvcc needed) when the environment has PSY_COMPILER=nvrtc.
  * No GPU is needed for this call.  cubin_path receives the path of the compiled module. */
 int psy_model_compile(const char* cuda_source, const char* include_dir, const char* cache_dir,
                       const char* extra_flags, char* cubin_path, size_t cubin_path_cap);

@@ -17,7 +17,7 @@ def build_library(force: bool = False) -> str:
         [os.path.join(_HERE, "..", "include", "psydiff_b200.h")]
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
-    cmd = [NVCC, "-shared"] + FLAGS + ["-o", out] + srcs
+    cmd = [NVCC, "-shared"] + FLAGS + ["-o", out] + srcs + ["-ldl"]
     subprocess.run(cmd, check=True)
     return out
 

@@ -24,6 +24,7 @@
 #include <thread>
 #include <unordered_map>
 #include <vector>
+#include <dlfcn.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -283,6 +284,62 @@ __global__ void __launch_bounds__(256) psy_dfma_peak(double* out, int iters, dou
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+// ---- optional in-process compile through NVRTC (PSY_COMPILER=nvrtc); libnvrtc is dlopen'ed, never linked ------------
+struct Nvrtc {
+  void* lib = nullptr;
+  int (*CreateProgram)(void**, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  int (*CompileProgram)(void*, int, const char* const*) = nullptr;
+  int (*GetCUBINSize)(void*, size_t*) = nullptr;
+  int (*GetCUBIN)(void*, char*) = nullptr;
+  int (*GetProgramLogSize)(void*, size_t*) = nullptr;
+  int (*GetProgramLog)(void*, char*) = nullptr;
+  int (*DestroyProgram)(void**) = nullptr;
+};
+Nvrtc g_nvrtc;
+
+bool load_nvrtc() {
+  if (g_nvrtc.lib) return true;
+  for (const char* name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"}) {
+    g_nvrtc.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+    if (g_nvrtc.lib) break;
+  }
+  if (!g_nvrtc.lib) return false;
+  struct { const char* n; void** f; } tab[] = {
+      {"nvrtcCreateProgram", (void**)&g_nvrtc.CreateProgram}, {"nvrtcCompileProgram", (void**)&g_nvrtc.CompileProgram},
+      {"nvrtcGetCUBINSize", (void**)&g_nvrtc.GetCUBINSize}, {"nvrtcGetCUBIN", (void**)&g_nvrtc.GetCUBIN},
+      {"nvrtcGetProgramLogSize", (void**)&g_nvrtc.GetProgramLogSize}, {"nvrtcGetProgramLog", (void**)&g_nvrtc.GetProgramLog},
+      {"nvrtcDestroyProgram", (void**)&g_nvrtc.DestroyProgram}};
+  for (auto& t : tab) {
+    *t.f = dlsym(g_nvrtc.lib, t.n);
+    if (!*t.f) { dlclose(g_nvrtc.lib); g_nvrtc.lib = nullptr; return false; }
+  }
+  return true;
+}
+
+// returns 0 and fills `cubin`, or an error code with the compiler log in `log`
+int nvrtc_compile(const char* src, const std::string& inc, const std::string& flags, std::string& cubin, std::string& log) {
+  if (!load_nvrtc()) { log = "libnvrtc not found"; return 1; }
+  void* prog = nullptr;
+  if (g_nvrtc.CreateProgram(&prog, src, "psy_model.cu", 0, nullptr, nullptr) != 0) { log = "nvrtcCreateProgram failed"; return 1; }
+  std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--include-path=" + inc};
+  std::stringstream ss(flags);
+  for (std::string tok; ss >> tok;) opts.push_back(tok);
+  std::vector<const char*> o;
+  for (auto& x : opts) o.push_back(x.c_str());
+  const int rc = g_nvrtc.CompileProgram(prog, (int)o.size(), o.data());
+  size_t ls = 0;
+  g_nvrtc.GetProgramLogSize(prog, &ls);
+  if (ls > 1) { log.resize(ls); g_nvrtc.GetProgramLog(prog, &log[0]); }
+  if (rc == 0) {
+    size_t cs = 0;
+    g_nvrtc.GetCUBINSize(prog, &cs);
+    cubin.resize(cs);
+    g_nvrtc.GetCUBIN(prog, &cubin[0]);
+  }
+  g_nvrtc.DestroyProgram(&prog);
+  return rc;
+}
+
 uint64_t fnv1a(const std::string& s, uint64_t h = 1469598103934665603ULL) {
   for (unsigned char c : s) { h ^= c; h *= 1099511628211ULL; }
   return h;
@@ -414,6 +471,9 @@ int psy_model_compile(const char* cuda_source, const char* include_dir, const ch
     h = fnv1a(body, h);
   }
   h = fnv1a(flags, h);
+  const char* comp_env = getenv("PSY_COMPILER");
+  const bool use_nvrtc = comp_env && std::string(comp_env) == "nvrtc";
+  if (use_nvrtc) h = fnv1a("nvrtc", h);
   char name[64];
   snprintf(name, sizeof name, "psy_%016llx", (unsigned long long)h);
   mkdir(cache.c_str(), 0755);
@@ -424,6 +484,24 @@ int psy_model_compile(const char* cuda_source, const char* include_dir, const ch
       std::ofstream f(cu);
       f << cuda_source;
       if (!f) return fail(PSY_ERR_COMPILE, "cannot write %s", cu.c_str());
+    }
+    if (use_nvrtc) {
+      std::string image, clog;
+      if (nvrtc_compile(cuda_source, inc, flags, image, clog) != 0) {
+        if (clog.size() > 3000) clog = clog.substr(0, 3000) + "\n...";
+        return fail(PSY_ERR_COMPILE,
+                    "model does not compile for the device (statements outside the supported equation subset are "
+                    "unsupported on device):\n%s", clog.c_str());
+      }
+      const std::string tmpn = cubin + ".tmp" + std::to_string((long long)getpid());
+      {
+        std::ofstream f(tmpn, std::ios::binary);
+        f.write(image.data(), (std::streamsize)image.size());
+        if (!f) return fail(PSY_ERR_COMPILE, "cannot write %s", tmpn.c_str());
+      }
+      if (rename(tmpn.c_str(), cubin.c_str()) != 0) return fail(PSY_ERR_COMPILE, "cannot move %s into the cache", tmpn.c_str());
+      strcpy(cubin_path, cubin.c_str());
+      return PSY_OK;
     }
     const char* nvcc_env = getenv("PSY_NVCC");
     std::string nvcc = nvcc_env ? nvcc_env : (file_exists("/usr/local/cuda/bin/nvcc") ? "/usr/local/cuda/bin/nvcc" : "nvcc");

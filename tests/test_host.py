@@ -289,3 +289,22 @@ def test_slot_map_equals_literal_parameter_table_on_random_groupings():
         assert pt.theta_labels == labels
         assert pt.theta_index.tolist() == idx
     check()
+
+
+def test_nvrtc_compile_path_matches_nvcc(monkeypatch):
+    """PSY_COMPILER=nvrtc: in-process compile of the same TU (no nvcc subprocess); same kernel resources."""
+    import subprocess
+    m = pd.newPsydiff(**synth.config_c1(N=2, T=3))
+    a = pd.compileModelSource(m)
+    monkeypatch.setenv("PSY_COMPILER", "nvrtc")
+    b = pd.compileModelSource(m)
+    assert a != b and os.path.getsize(b) > 10000
+
+    def res(path):
+        out = subprocess.run(["cuobjdump", "-res-usage", path], capture_output=True, text=True).stdout
+        return re.search(r"REG:(\d+) STACK:(\d+)", out).groups()
+    assert res(a)[1] == res(b)[1] and abs(int(res(a)[0]) - int(res(b)[0])) <= 8
+    kw = synth.config_c1(N=2, T=3)
+    kw["latentEquations"] = "arma::mat E = arma::expmat(DRIFT); dx = E*x;"
+    with pytest.raises(PsydiffError, match="unsupported on device"):
+        pd.compileModelSource(pd.newPsydiff(**kw))
