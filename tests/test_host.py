@@ -308,3 +308,67 @@ def test_nvrtc_compile_path_matches_nvcc(monkeypatch):
     kw["latentEquations"] = "arma::mat E = arma::expmat(DRIFT); dx = E*x;"
     with pytest.raises(PsydiffError, match="unsupported on device"):
         pd.compileModelSource(pd.newPsydiff(**kw))
+
+
+def test_all_exported_primitives_against_numpy():
+    """The 21 host primitives of the C ABI (src/exposeInlineFunctions.cpp names) against their numpy definitions."""
+    from oracle import numpy_ref as nr
+    L = _lib.lib()
+    rng = np.random.default_rng(11)
+    n, m = 4, 3
+    s = 2 * n + 1
+    F = np.asfortranarray
+    d = _lib.dptr
+    wm, wc = np.zeros(s), np.zeros(s)
+    L.psy_getMeanWeights(n, .3, 2., 1., d(wm)); L.psy_getCovWeights(n, .3, 2., 1., d(wc))
+    assert np.allclose(wm, nr.getMeanWeights(n, .3, 2., 1.)) and np.allclose(wc, nr.getCovWeights(n, .3, 2., 1.))
+    W = F(np.zeros((s, s)))
+    L.psy_getWMatrix(s, d(wm), d(wc), d(W))
+    assert np.allclose(W, nr.getWMatrix(wm, wc))
+    c = .09 * (n + 1)
+    A = F(np.tril(rng.standard_normal((n, n))) + 2 * np.eye(n))
+    mvec = rng.standard_normal(n)
+    X = F(np.zeros((n, s)))
+    assert L.psy_getSigmaPoints(n, d(mvec), d(A), 1, c, d(X)) == 0
+    assert np.allclose(X, nr.getSigmaPoints(mvec, A, c))
+    P = F(A @ A.T)
+    X2 = F(np.zeros((n, s)))
+    assert L.psy_getSigmaPoints(n, d(mvec), d(P), 0, c, d(X2)) == 0 and np.allclose(X2, X)      # chol(P) inside
+    assert L.psy_getSigmaPoints(n, d(mvec), d(F(-np.eye(n))), 0, c, d(X2)) != 0                   # not positive definite
+    mean = np.zeros(n)
+    L.psy_computeMeanFromSigmaPoints(n, s, d(X), d(wm), d(mean))
+    assert np.allclose(mean, X @ wm)
+    A2, P2 = F(np.zeros((n, n))), F(np.zeros((n, n)))
+    L.psy_getAFromSigmaPoints(n, d(X), d(wm), c, d(A2)); L.psy_computePFromSigmaPoints(n, d(X), d(wm), c, d(P2))
+    assert np.allclose(A2, A) and np.allclose(P2, A @ A.T)
+    Mx, Phi = F(rng.standard_normal((n, n))), F(np.zeros((n, n)))
+    L.psy_getPhi(n, d(Mx), d(Phi))
+    assert np.allclose(Phi, nr.getPhi(Mx))
+    Y = F(rng.standard_normal((m, s)))
+    R = F(np.diag([.3, .4, .5]))
+    mu, S, Cm = np.zeros(m), F(np.zeros((m, m))), F(np.zeros((n, m)))
+    L.psy_predictMu(m, s, d(Y), d(wm), d(mu)); L.psy_predictS(m, s, d(Y), d(W), d(R), d(S)); L.psy_predictC(n, m, s, d(X), d(Y), d(W), d(Cm))
+    assert np.allclose(mu, Y @ wm) and np.allclose(S, Y @ W @ Y.T + R) and np.allclose(Cm, X @ W @ Y.T)
+    Spd = F(S @ S.T + np.eye(m))
+    K = F(np.zeros((n, m)))
+    assert L.psy_computeK(n, m, d(Cm), d(Spd), d(K)) == 0 and np.allclose(K, Cm @ np.linalg.inv(Spd))
+    res = rng.standard_normal(m)
+    mu2, Pu = np.zeros(n), F(np.zeros((n, n)))
+    L.psy_updateM(n, m, d(mvec), d(K), d(res), d(mu2)); L.psy_updateP(n, m, d(P), d(K), d(Spd), d(Pu))
+    assert np.allclose(mu2, mvec + K @ res) and np.allclose(Pu, P - K @ Spd @ K.T)
+    srS = F(np.linalg.cholesky(Spd))
+    Ksr = F(np.zeros((n, m)))
+    assert L.psy_computeK_SR(n, m, d(Cm), d(srS), d(Ksr)) == 0 and np.allclose(Ksr, K)
+    out = C.c_double()
+    L.psy_computeIndividualM2LLChol(m, d(res), d(mu), d(srS), C.byref(out))
+    assert out.value == pytest.approx(nr.m2ll_chol(m, res, mu, srS))
+    sr2, want = F(np.zeros((m, m))), nr.predictSquareRootOfS(Y, mu, np.asarray(R), wc[0], wc[1])
+    L.psy_predictSquareRootOfS(m, s, d(Y), d(mu), d(R), wc[0], wc[1], d(sr2))
+    assert np.allclose(sr2, want)                      # Givens here, LAPACK Householder there: signs normalised by cholupdate (T3)
+    Lc = F(np.linalg.cholesky(Spd)); x = rng.standard_normal(m) * .2
+    want = nr.cholupdate(np.array(Lc), x, 2.0, "downdate")
+    assert L.psy_cholupdate(m, d(Lc), d(x), 2.0, b"downdate") == 0 and np.allclose(np.tril(Lc), np.tril(want))
+    lc, ch = F(rng.standard_normal((n, n))), F(np.zeros((n, n)))
+    L.psy_logChol2Chol(n, d(lc), d(ch))
+    exp = np.array(lc); exp[np.diag_indices(n)] = np.exp(np.diag(lc))
+    assert np.allclose(ch, exp)
