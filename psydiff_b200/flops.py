@@ -23,9 +23,9 @@ def rhs_flops(n: int, Ff: int, l_diag: bool = True, dep=None) -> int:
             f += 2 * (i - j - 1)
     f += (2 * n + 1) * Ff        # drift at every sigma point
     f += 4 * tn                  # sigma points m ± sqrt(c) A_j (two FMAs per element)
-    f += 3 * sum(moved[i][j] for i in range(n) for j in range(n))              # d = fp - fm, fs += fp + fm
+    f += 4 * sum(moved[i][j] for i in range(n) for j in range(n))              # d = fp - fm; dm += wm1 (fp + fm)
     f += 2 * sum(moved[k][j] for j in range(n) for i in range(n) for k in range(i))   # G~[:, j] = W d_j
-    f += 3 * n                   # dm
+    f += n                       # dm seed: (wm0 + 2 wm1 #unmoved) f0
     f += n                       # kap * A_jj
     if l_diag:
         f += off                 # Bq = W diag(q)
@@ -42,13 +42,13 @@ def rhs_flops(n: int, Ff: int, l_diag: bool = True, dep=None) -> int:
     f += 3 * n + 4 * off         # fold kap (G~ D + D G~') into Phi, halve the diagonal
     for i in range(n):           # dA = (A~ Phi) D^-1
         for j in range(i + 1):
-            f += 2 * (i - j) + 1
+            f += 2 * (i - j)     # the D^-1 column scaling is folded into the RK4 coefficients (step_flops)
     return f
 
 
 def step_flops(n: int, Ff: int, l_diag: bool = True, dep=None) -> int:
     ns = n + n * (n + 1) // 2
-    return 4 * rhs_flops(n, Ff, l_diag, dep) + 4 * 4 * ns
+    return 4 * rhs_flops(n, Ff, l_diag, dep) + 4 * (4 * ns + 2 * n)
 
 
 def update_flops(n: int, m: int, Fh: int) -> int:
