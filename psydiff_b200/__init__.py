@@ -12,3 +12,8 @@ from .optim import (  # noqa: F401,E402
     psydiffFitInternal, psydiffGradientsInternal, psydiffOptimBFGS, psydiffOptimNelderMead, psydiffOptimx, extractOptimx, psydiffDEoptim, psydiffSubplex, psydiffNLopt,
     getStandardErrors, GIST, getRegValue, getSubgradients, bestOfN, getDataTemplate, simulateData,
 )
+from .primitives import (  # noqa: F401,E402
+    getSigmaPoints, getMeanWeights, getCovWeights, getWMatrix, computeMeanFromSigmaPoints, getAFromSigmaPoints,
+    computePFromSigmaPoints, getPhi, predictMu, predictS, predictC, computeK, updateM, updateP, computeIndividualM2LL,
+    cholupdate, qr_, logChol2Chol, setParameterList,
+)

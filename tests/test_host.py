@@ -372,3 +372,41 @@ def test_all_exported_primitives_against_numpy():
     L.psy_logChol2Chol(n, d(lc), d(ch))
     exp = np.array(lc); exp[np.diag_indices(n)] = np.exp(np.diag(lc))
     assert np.allclose(ch, exp)
+
+
+def test_python_mirror_exports_all_22_reference_functions():
+    """R/RcppExports.R:12-257 lists 22 exported functions; the mirror offers every one under the same name and arguments."""
+    import inspect
+    ref = {"setParameterValues": ["parameterTable", "parameterValues", "parameterLabels"], "getParameterValues": ["psydiffModel"],
+           "setParameterList": ["parameterTable", "parameterList", "person"], "getSigmaPoints": ["m", "A", "covarianceIsRoot", "c"],
+           "getMeanWeights": ["n", "alpha", "beta", "kappa"], "getCovWeights": ["n", "alpha", "beta", "kappa"],
+           "getWMatrix": ["meanWeights", "covWeights"], "computeMeanFromSigmaPoints": ["sigmaPoints", "meanWeights"],
+           "getAFromSigmaPoints": ["sigmaPoints", "meanWeights", "c"], "computePFromSigmaPoints": ["sigmaPoints", "meanWeights", "c"],
+           "getPhi": ["squareMatrix"], "predictMu": ["Y_", "meanWeights"], "predictS": ["Y_", "W", "R"], "predictC": ["sigmaPoints", "Y_", "W"],
+           "computeK": ["C_", "S"], "updateM": ["m_", "K", "residual"], "updateP": ["P_", "K", "S"],
+           "computeIndividualM2LL": ["nObservedVariables", "rawData", "expectedMeans", "expectedCovariance"],
+           "cholupdate": ["L", "x", "v", "direction"], "qr_": ["X"], "logChol2Chol": ["logChol"], "clonePsydiffModel": ["model"]}
+    assert len(ref) == 22
+    for name, args in ref.items():
+        fn = getattr(pd, name)
+        assert list(inspect.signature(fn).parameters)[:len(args)] == args, name
+    # a few calls through the mirror
+    A = np.array([[2.0, 0.0], [0.5, 1.5]])
+    X = pd.getSigmaPoints([1.0, 2.0], A, True, 0.08)
+    wm = pd.getMeanWeights(2, .2, 2., 0.)
+    assert np.allclose(pd.getAFromSigmaPoints(X, wm, 0.08), A) and np.allclose(pd.computePFromSigmaPoints(X, wm, 0.08), A @ A.T)
+    assert np.allclose(pd.logChol2Chol(np.array([[np.log(2.0), 0.0], [0.5, np.log(1.5)]])), A)
+    L2 = pd.cholupdate(A, [0.3, 0.1], 1.0, "update")
+    assert np.allclose(np.tril(L2) @ np.tril(L2).T, A @ A.T + np.outer([0.3, 0.1], [0.3, 0.1]))
+    with pytest.raises(PsydiffError, match="Unknown direction"):
+        pd.cholupdate(A, [0.3, 0.1], 1.0, "sideways")
+    S = A @ A.T
+    assert pd.computeIndividualM2LL(2, [0.1, -0.2], [0.0, 0.0], S) == pytest.approx(
+        2 * np.log(2 * np.pi) + np.linalg.slogdet(S)[1] + np.array([0.1, -0.2]) @ np.linalg.solve(S, [0.1, -0.2]))
+    m = pd.newPsydiff(**synth.config_c1(N=3, T=4))
+    pt, plist = m["pars"]["parameterTable"], m["pars"]["parameterList"]
+    pd.setParameterValues(pt, {"drift_eta1": -0.9, "mm_Y2": 0.7})
+    pd.setParameterList(pt, plist, 2)
+    assert plist["DRIFT"][0, 0] == -0.9 and plist["MANIFESTMEANS"][1, 0] == 0.7
+    with pytest.raises(PsydiffError, match="not found in data set"):
+        pd.setParameterList(pt, plist, 99)
