@@ -6,11 +6,12 @@ from ._lib import PsydiffError  # noqa: F401
 from .model import (  # noqa: F401
     newPsydiff, compileModel, compileModelSource, uploadData, fitModel, fitTotals, getGradients, getGradient, getGradientsParallel,
     compileParallelGradients, stopParallelGradients, getParameterValues, setParameterValues, clonePsydiffModel,
-    sdeModelMatrix, sepNameFromValue, chol2LogChol, extractParameters, makeGroups, checkEquation,
+    sdeModelMatrix, sepNameFromValue, chol2LogChol, extractParameters, makeGroups, checkEquation, fromMxMatrix,
 )
+from .codegen import modelTemplate, prepareEquations  # noqa: F401,E402
 from .optim import (  # noqa: F401,E402
     psydiffFitInternal, psydiffGradientsInternal, psydiffOptimBFGS, psydiffOptimNelderMead, psydiffOptimx, extractOptimx, psydiffDEoptim, psydiffSubplex, psydiffNLopt,
-    getStandardErrors, GIST, getRegValue, getSubgradients, bestOfN, getDataTemplate, simulateData,
+    getStandardErrors, GIST, getRegValue, getSubgradients, bestOfN, getDataTemplate, simulateData, fitf,
 )
 from .primitives import (  # noqa: F401,E402
     getSigmaPoints, getMeanWeights, getCovWeights, getWMatrix, computeMeanFromSigmaPoints, getAFromSigmaPoints,

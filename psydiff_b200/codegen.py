@@ -130,6 +130,38 @@ def drift_dependency(spec: ModelSpec) -> List[int]:
     return [0 if v is None else v for v in mask]        # a component never assigned stays 0 (dx is zero-initialised)
 
 
+def modelTemplate(srUpdate: bool = True) -> str:
+    """modelTemplate (R/modelTemplate.R:5-1011): the source template of a model translation unit.  The reference's template is
+    Rcpp/Armadillo/odeint C++ with the person x time loop written out; here it is a CUDA TU whose filter lives in
+    psy_filter.cuh and whose model struct receives the user's equations.  LATENTEQUATIONPLACEHOLDER and
+    MEASUREMENTEQUATIONPLACEHOLDER are replaced exactly as newPsydiff does (R/prepareModel.R:509-512); the remaining
+    upper-case placeholders carry the compile-time facts the reference reads from the model list at run time."""
+    return (
+        "// generated by psydiff_b200.codegen — model translation unit for sm_100a\n"
+        '#include "psy_filter.cuh"\n\n'
+        "struct PsyUserModel {\n"
+        "  static constexpr int N = NLATENTPLACEHOLDER, M = NMANIFESTPLACEHOLDER, NSLOT = NSLOTPLACEHOLDER, NFREE = NFREEPLACEHOLDER;\n"
+        "  static constexpr int L_STRUCT = LSTRUCTPLACEHOLDER;\n"
+        "  static constexpr bool R_DIAG = RDIAGPLACEHOLDER;\n"
+        f"  static constexpr bool SR = {'true' if srUpdate else 'false'};\n"
+        "  static constexpr int STEPPER = STEPPERPLACEHOLDER;\n"
+        "  // bit r of dep(i): drift component i may read x_r (Jacobian sparsity read off the equation text)\n"
+        "  static __host__ __device__ constexpr unsigned dep(int i) { return DEPPLACEHOLDER; }\n\n"
+        "LATENTEQUATIONPLACEHOLDER\n"
+        "MEASUREMENTEQUATIONPLACEHOLDER\n"
+        "INITIALPLACEHOLDER"
+        "};\n\nPSY_INSTANTIATE(PsyUserModel)\n")
+
+
+def prepareEquations(equations: str, spec: ModelSpec) -> str:
+    """prepareEquations (R/prepareModel.R:737-770): declarations of every parameter container the text refers to, followed
+    by the user's statements.  The reference emits `arma::mat X = modelPars["X"];` lookups; here the containers are
+    fixed-size values whose free entries read the instance's slot array."""
+    out = [_bind(spec.container(name)) for name in referenced(equations, spec)]
+    out.append("    " + equations.strip().replace("\n", "\n    ") + "\n")
+    return "".join(out)
+
+
 def emit_cuda(spec: ModelSpec) -> str:
     n, m, F = spec.nlatent, spec.nmanifest, spec.n_slots
     A0, Ll, Rl, m0 = (spec.container(k) for k in ("A0LogChol", "LLogChol", "RLogChol", "m0"))
@@ -145,53 +177,40 @@ def emit_cuda(spec: ModelSpec) -> str:
                          "entries above the diagonal are unsupported on device")
     l_diag, _ = _structure(Ll)
     r_diag, _ = _structure(Rl)
-    src = []
-    src.append("// generated by psydiff_b200.codegen — model translation unit for sm_100a\n")
-    src.append('#include "psy_filter.cuh"\n\n')
-    src.append("struct PsyUserModel {\n")
-    src.append(f"  static constexpr int N = {n}, M = {m}, NSLOT = {F}, NFREE = {max(F, 1)};\n")
-    src.append(f"  static constexpr int L_STRUCT = {'psy::L_DIAG' if l_diag else 'psy::L_FULL'};\n")
-    src.append(f"  static constexpr bool R_DIAG = {'true' if r_diag else 'false'};\n")
-    src.append(f"  static constexpr bool SR = {'true' if spec.srUpdate else 'false'};\n")
-    src.append(f"  static constexpr int STEPPER = {int(spec.stepper)};\n")
     dep = drift_dependency(spec)
     chain = " : ".join(f"i == {i} ? {hex(dep[i])}u" for i in range(n - 1)) + (" : " if n > 1 else "") + f"{hex(dep[n - 1])}u"
-    src.append("  // bit r of dep(i): drift component i may read x_r (Jacobian sparsity read off the equation text)\n")
-    src.append(f"  static __host__ __device__ constexpr unsigned dep(int i) {{ return {chain}; }}\n\n")
-    # latentEquation (R/prepareModel.R:493-505)
-    src.append("  static __device__ __forceinline__ void latentEquation(const psy::Vec<N>& x, psy::Vec<N>& dx,\n"
-               "      const double (&psy_p_)[NFREE], const int person, const double t) {\n")
-    for name in referenced(spec.latentEquations, spec):
-        src.append(_bind(spec.container(name)))
-    src.append("    " + spec.latentEquations.strip().replace("\n", "\n    ") + "\n")
-    src.append("  }\n\n")
-    # measurementEquation (R/prepareModel.R:479-491)
-    src.append("  static __device__ __forceinline__ void measurementEquation(const psy::Vec<N>& x, psy::Vec<M>& y,\n"
-               "      const double (&psy_p_)[NFREE], const int person, const double t) {\n")
-    for name in referenced(spec.manifestEquations, spec):
-        src.append(_bind(spec.container(name)))
-    src.append("    " + spec.manifestEquations.strip().replace("\n", "\n    ") + "\n")
-    src.append("  }\n\n")
-    # initial state: m0, A0LogChol, LLogChol as stored (log-Cholesky; the kernel applies logChol2Chol_C)
-    src.append("  static __device__ __forceinline__ void initial(double (&m0)[N], double (&A0lc)[N * N], double (&Llc)[N * N],\n"
-               "      const double (&psy_p_)[NFREE]) {\n")
+    # latentEquation (R/prepareModel.R:493-505) / measurementEquation (R/prepareModel.R:479-491)
+    latent = ("  static __device__ __forceinline__ void latentEquation(const psy::Vec<N>& x, psy::Vec<N>& dx,\n"
+              "      const double (&psy_p_)[NFREE], const int person, const double t) {\n"
+              + prepareEquations(spec.latentEquations, spec) + "  }\n")
+    manifest = ("  static __device__ __forceinline__ void measurementEquation(const psy::Vec<N>& x, psy::Vec<M>& y,\n"
+                "      const double (&psy_p_)[NFREE], const int person, const double t) {\n"
+                + prepareEquations(spec.manifestEquations, spec) + "  }\n")
+    # initial state: m0, A0LogChol, LLogChol as stored (log-Cholesky; the kernel applies logChol2Chol_C); Rchol = logChol2Chol(RLogChol)
+    ini = ["  static __device__ __forceinline__ void initial(double (&m0)[N], double (&A0lc)[N * N], double (&Llc)[N * N],\n"
+           "      const double (&psy_p_)[NFREE]) {\n"]
     m0v, m0s = m0.values.reshape(-1, order="F"), m0.slots.reshape(-1, order="F")
     for i in range(n):
         e = f"psy_p_[{int(m0s[i])}]" if m0s[i] >= 0 else lit(m0v[i])
-        src.append(f"    m0[{i}] = {e};\n")
+        ini.append(f"    m0[{i}] = {e};\n")
     for j in range(n):
         for i in range(n):
-            src.append(f"    A0lc[{i + j * n}] = {_elem(A0, i, j)};\n")
+            ini.append(f"    A0lc[{i + j * n}] = {_elem(A0, i, j)};\n")
     for j in range(n):
         for i in range(n):
-            src.append(f"    Llc[{i + j * n}] = {_elem(Ll, i, j)};\n")
-    src.append("  }\n\n")
-    # Rchol = logChol2Chol(RLogChol)
-    src.append("  static __device__ __forceinline__ void rchol(double (&Rc)[M * M], const double (&psy_p_)[NFREE]) {\n")
+            ini.append(f"    Llc[{i + j * n}] = {_elem(Ll, i, j)};\n")
+    ini.append("  }\n\n")
+    ini.append("  static __device__ __forceinline__ void rchol(double (&Rc)[M * M], const double (&psy_p_)[NFREE]) {\n")
     for j in range(m):
         for i in range(m):
             e = _elem(Rl, i, j)
-            src.append(f"    Rc[{i + j * m}] = {'exp(' + e + ')' if i == j else e};\n")
-    src.append("  }\n")
-    src.append("};\n\nPSY_INSTANTIATE(PsyUserModel)\n")
-    return "".join(src)
+            ini.append(f"    Rc[{i + j * m}] = {'exp(' + e + ')' if i == j else e};\n")
+    ini.append("  }\n")
+    code = modelTemplate(spec.srUpdate)
+    for key, val in (("NLATENTPLACEHOLDER", str(n)), ("NMANIFESTPLACEHOLDER", str(m)), ("NSLOTPLACEHOLDER", str(F)),
+                     ("NFREEPLACEHOLDER", str(max(F, 1))), ("LSTRUCTPLACEHOLDER", "psy::L_DIAG" if l_diag else "psy::L_FULL"),
+                     ("RDIAGPLACEHOLDER", "true" if r_diag else "false"), ("STEPPERPLACEHOLDER", str(int(spec.stepper))),
+                     ("DEPPLACEHOLDER", chain), ("MEASUREMENTEQUATIONPLACEHOLDER", manifest),
+                     ("LATENTEQUATIONPLACEHOLDER", latent), ("INITIALPLACEHOLDER", "".join(ini))):
+        code = code.replace(key, val)      # stringr::str_replace_all, R/prepareModel.R:511-512
+    return code

@@ -74,6 +74,19 @@ def sdeModelMatrix(values, labels):
     return out
 
 
+def fromMxMatrix(mxMatrixObject):
+    """fromMxMatrix (R/prepareModel.R:772-781): an OpenMx-style matrix object (``values`` and ``labels`` of equal shape, given
+    as attributes or dict entries; missing labels None/NaN) -> the "label = value" character matrix newPsydiff accepts."""
+    get = (lambda k: mxMatrixObject[k]) if isinstance(mxMatrixObject, dict) else (lambda k: getattr(mxMatrixObject, k))
+    values, labels = np.asarray(get("values"), dtype=float), np.asarray(get("labels"), dtype=object)
+    out = np.empty(values.shape, dtype=object)
+    for idx in np.ndindex(values.shape):
+        lab = labels[idx]
+        na = lab is None or (isinstance(lab, float) and np.isnan(lab))
+        out[idx] = repr(float(values[idx])) if na else f"{lab} = {float(values[idx])!r}"
+    return out
+
+
 def chol2LogChol(matValues, matLabels, sanityChecks=True, matrixName=""):
     """R/prepareModel.R:820-842: log-Cholesky parameterisation; diagonal labels get the prefix "ln"."""
     vals = np.array(matValues, dtype=float)

@@ -226,6 +226,12 @@ def getStandardErrors(model, ndeps: float = 1e-3) -> Dict[str, float]:
     return dict(zip(names, se))
 
 
+def fitf(pars: Dict[str, float], model) -> float:
+    """fitf (R/GIST.R:285-289): Σ -2LL at the named parameter vector."""
+    setParameterValues(model["pars"]["parameterTable"], pars)
+    return float(np.sum(fitModel(model)["m2LL"]))
+
+
 # ---------------------------------------------------------------------------------------------------------- GIST
 def getRegValue(lambda_, theta: Dict[str, float], regIndicators: Sequence[str], adaptiveLassoWeights=None) -> float:
     """getRegValue (R/GIST.R:337-363): Σ lambda * w_i * |theta_i| over the regularised parameters."""

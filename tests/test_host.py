@@ -410,3 +410,18 @@ def test_python_mirror_exports_all_22_reference_functions():
     assert plist["DRIFT"][0, 0] == -0.9 and plist["MANIFESTMEANS"][1, 0] == 0.7
     with pytest.raises(PsydiffError, match="not found in data set"):
         pd.setParameterList(pt, plist, 99)
+
+
+def test_model_template_and_helpers():
+    t = pd.modelTemplate(True)
+    assert "LATENTEQUATIONPLACEHOLDER" in t and "MEASUREMENTEQUATIONPLACEHOLDER" in t and "SR = true" in t
+    assert "SR = false" in pd.modelTemplate(False)
+    m = pd.newPsydiff(**synth.config_c1(N=2, T=3))
+    pre = pd.prepareEquations("dx = DRIFT*x;", m["_spec"])
+    assert "psy::Mat<2,2> DRIFT;" in pre and pre.rstrip().endswith("dx = DRIFT*x;")
+    assert "PLACEHOLDER" not in m["cppCode"]
+    mx = {"values": np.array([[-0.3, 0.0], [0.2, -0.5]]), "labels": np.array([["a", None], ["b", "c"]], dtype=object)}
+    out = pd.fromMxMatrix(mx)
+    assert out[0, 0] == "a = -0.3" and out[0, 1] == "0.0" and out[1, 1] == "c = -0.5"
+    s = pd.sepNameFromValue(out)
+    assert s["labels"][1, 0] == "b" and s["values"][1, 0] == 0.2
