@@ -110,7 +110,7 @@ def integrate_const_rk4(X, t1, h, f):              # Boost.odeint integrate_cons
     return X
 
 
-def fit_person(obs, dts, drift, meas, pars, person, m0, A0, Lmat, Rchol, alpha=.2, beta=2.0, kappa=0.0, h=1 / 30):
+def fit_person(obs, dts, drift, meas, pars, person, m0, A0, Lmat, Rchol, alpha=.2, beta=2.0, kappa=0.0, h=1 / 30, stepper="rk4"):
     """Body of fitModel's person loop, SR variant (R/modelTemplate.R:244-411).  Returns (-2LL, latentScores, predictedManifest)."""
     n = len(m0)
     if n + kappa == 0:
@@ -128,7 +128,8 @@ def fit_person(obs, dts, drift, meas, pars, person, m0, A0, Lmat, Rchol, alpha=.
         m_ = m.copy()
         X = getSigmaPoints(m_, A, c)
         if abs(dts[tp]) > 0:
-            X = integrate_const_rk4(X, dts[tp], h, lambda Z, t: rhs(Z, t, drift, pars, person, wm, wc, c, Lmat))
+            g = lambda Z, t: rhs(Z, t, drift, pars, person, wm, wc, c, Lmat)
+            X = integrate_const_rk4(X, dts[tp], h, g) if stepper == "rk4" else integrate_dopri5(X, dts[tp], h, g)
             m_ = X[:, 0].copy()
             A = np.tril(getAFromSigmaPoints(X, wm, c))
         Y = np.column_stack([meas(X[:, i], pars, person, tsum) for i in range(X.shape[1])])
@@ -148,3 +149,39 @@ def fit_person(obs, dts, drift, meas, pars, person, m0, A0, Lmat, Rchol, alpha=.
             m = m_
         lat.append(m.copy())
     return m2ll, np.array(lat), np.array(pred)
+
+
+# ---- Boost.odeint integrate() = integrate_adaptive(controlled_runge_kutta<runge_kutta_dopri5>, 1e-6, 1e-6) — rule T2 --------
+_DP_C = [0.0, 1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0]
+_DP_A = [[], [1 / 5], [3 / 40, 9 / 40], [44 / 45, -56 / 15, 32 / 9], [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+         [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656], [35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84]]
+_DP_B5 = np.array([35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0.0])
+_DP_B4 = np.array([5179 / 57600, 0.0, 7571 / 16695, 393 / 640, -92097 / 339200, 187 / 2100, 1 / 40])
+
+
+def integrate_dopri5(X, t1, dt, f, eps_abs=1e-6, eps_rel=1e-6):
+    """Adaptive Dormand–Prince 5(4) with odeint's default controller; state X may be any array (max-norm over all entries)."""
+    t = 0.0
+    k1 = f(X, t)
+    while t1 - t > DBL_EPS:
+        if (t + dt) - t1 > DBL_EPS:
+            dt = t1 - t
+        for _ in range(500):
+            ks = [k1]
+            for s in range(1, 7):
+                Xs = X + dt * sum(a * k for a, k in zip(_DP_A[s], ks))
+                ks.append(f(Xs, t + _DP_C[s] * dt))
+            Xn = X + dt * sum(b * k for b, k in zip(_DP_B5[:6], ks[:6]))     # = the stage-7 point (FSAL)
+            xerr = dt * sum((b5 - b4) * k for b5, b4, k in zip(_DP_B5, _DP_B4, ks))
+            err = np.max(np.abs(xerr) / (eps_abs + eps_rel * (np.abs(X) + abs(dt) * np.abs(k1))))
+            if err > 1.0:
+                dt *= max(0.9 * err ** (-1 / 3), 0.2)
+                continue
+            t += dt
+            if err < 0.5:
+                dt *= 0.9 * max(5.0 ** -5, err) ** (-1 / 5)
+            X, k1 = Xn, ks[6]
+            break
+        else:
+            raise RuntimeError("step size underflow")
+    return X
