@@ -185,3 +185,46 @@ def integrate_dopri5(X, t1, dt, f, eps_abs=1e-6, eps_rel=1e-6):
         else:
             raise RuntimeError("step size underflow")
     return X
+
+
+def fit_person_cov(obs, dts, drift, meas, pars, person, m0, A0, Lmat, Rchol, alpha=.2, beta=2.0, kappa=0.0, h=1 / 30):
+    """Covariance variant of fitModel's person loop (srUpdate = FALSE, R/modelTemplate.R:660-838): chol(P) per time point,
+    S = Y W Y' + R symmetrised, K = C inv(S), P = P_ - K S K' symmetrised, det-based -2LL (psydiffInternals.h:103-115)."""
+    n = len(m0)
+    if n + kappa == 0:
+        kappa -= 1
+    c = alpha ** 2 * (n + kappa)
+    wm, wc = getMeanWeights(n, alpha, beta, kappa), getCovWeights(n, alpha, beta, kappa)
+    W = getWMatrix(wm, wc)
+    m = m0.astype(float).copy()
+    P = A0 @ A0.T
+    R = Rchol @ Rchol.T
+    m2ll, tsum, lat = 0.0, 0.0, []
+    for tp in range(len(dts)):
+        tsum += dts[tp]
+        ob = obs[tp]
+        nm = np.flatnonzero(np.isfinite(ob))
+        m_, P_ = m.copy(), P.copy()
+        A = np.linalg.cholesky(P_)
+        X = getSigmaPoints(m_, A, c)
+        if abs(dts[tp]) > 0:
+            X = integrate_const_rk4(X, dts[tp], h, lambda Z, t: rhs(Z, t, drift, pars, person, wm, wc, c, Lmat))
+            m_ = X[:, 0].copy()
+            Af = getAFromSigmaPoints(X, wm, c)
+            P_ = Af @ Af.T
+        Y = np.column_stack([meas(X[:, i], pars, person, tsum) for i in range(X.shape[1])])
+        mu = Y @ wm
+        if len(nm) > 0:
+            S = Y[nm] @ W @ Y[nm].T + R[np.ix_(nm, nm)]
+            S = (S + S.T) / 2
+            C = X @ W @ Y[nm].T
+            K = C @ np.linalg.inv(S)
+            r = (ob - mu)[nm]
+            m = m_ + K @ r
+            P = P_ - K @ S @ K.T
+            P = (P + P.T) / 2
+            m2ll += len(nm) * np.log(2 * np.pi) + np.log(np.linalg.det(S)) + float(r @ np.linalg.inv(S) @ r)
+        else:
+            m, P = m_, (P_ + P_.T) / 2
+        lat.append(m.copy())
+    return m2ll, np.array(lat)

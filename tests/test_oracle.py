@@ -174,6 +174,7 @@ def test_cpp_oracle_vs_numpy_lapack_restatement():
     def meas(x, p, person, t):
         return np.array([x[0] + 0.15 * x[0] * x[0], np.exp(0.3 * x[1]) + 0.1 * np.sin(t)])
     ref5 = Oracle(pd.newPsydiff(**dict(kw, integrateFunction="runge_kutta_dopri5"))).fit()      # rule T2: adaptive dopri5
+    refc = Oracle(pd.newPsydiff(**dict(kw, srUpdate=False))).fit()                              # covariance variant (a24)
     assert np.max(np.abs(ref5["m2LL"] - ref["m2LL"]) / np.abs(ref["m2LL"])) > 1e-9               # a different integrator ...
     for p in range(N):
         sl = slice(p * T, (p + 1) * T)
@@ -186,3 +187,6 @@ def test_cpp_oracle_vs_numpy_lapack_restatement():
                                     np.array(kw["L"]), np.array(kw["Rchol"]), h=0.05, stepper="dopri5")
         assert abs(f5 - ref5["m2LL"][p]) / abs(f5) < 1e-11                                       # ... restated twice, same numbers
         assert np.max(np.abs(lat5 - ref5["latentScores"][sl])) < 1e-10
+        fc, latc = nr.fit_person_cov(obs[sl], dt[sl], drift, meas, None, p + 1, np.array([1.0, 0.5]), np.array(kw["A0"]),
+                                     np.array(kw["L"]), np.array(kw["Rchol"]), h=0.05)
+        assert abs(fc - refc["m2LL"][p]) / abs(fc) < 1e-11 and np.max(np.abs(latc - refc["latentScores"][sl])) < 1e-10
