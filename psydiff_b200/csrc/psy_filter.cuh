@@ -57,7 +57,11 @@ __device__ __forceinline__ double rcp(double x) {
   return 1.0 / x;
 #else
   double r;
+#ifdef __CUDA_ARCH__
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#else
+  r = psy_sim_rcp_seed(x);  // host compile of this header = tests/hostsim (kernel-source emulation in the CPU test suite)
+#endif
   double e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   e = fma(-x, r, 1.0);
