@@ -46,6 +46,31 @@ int psy_version(void);
  * kernel uses per observation interval; the remainder of the interval is not integrated. */
 int psy_rk4_step_count(double t1, double h);
 
+/* ---- newPsydiff's source assembly (R/prepareModel.R:479-512, 737-770; template R/modelTemplate.R:5-1011) ----------
+ * The reference pastes prepareEquations(latentEquations) and prepareEquations(manifestEquations) into modelTemplate()
+ * and stores the text in model$cppCode.  psy_emit_model_source does the same for the CUDA translation unit: every entry
+ * of model$pars$parameterList the statements name is declared as a fixed-size container whose free elements read the
+ * instance's slot array, and m0 / A0LogChol / LLogChol / RLogChol become the initial-state functions of the model struct.
+ * Pure host string work, callable from any language; the result goes to psy_model_compile. */
+typedef struct psy_container {
+  const char* name;     /* name in model$pars$parameterList; "m0", "A0LogChol", "LLogChol", "RLogChol" must be present */
+  int is_scalar;        /* targetClass "double" (1) or "matrix" (0) (R/prepareModel.R:646-690) */
+  int rows, cols;
+  const double* values; /* column-major start values */
+  const int* slots;     /* column-major: 0-based row of parameterTableInit for a free element, -1 for a fixed one */
+} psy_container;
+/* out/cap: destination buffer; *needed (may be NULL) receives the size including the terminator; out == NULL with
+ * needed != NULL only queries the size. */
+int psy_emit_model_source(int n, int m, int n_slots, const char* latent_equations, const char* manifest_equations,
+                          const psy_container* containers, int n_containers, int sr_update, int stepper, char* out,
+                          size_t cap, size_t* needed);
+/* modelTemplate() (R/modelTemplate.R:5): the template text with its upper-case placeholders */
+int psy_model_template(int sr_update, char* out, size_t cap, size_t* needed);
+/* Jacobian sparsity of the drift as read off the statements: bit r of mask[i] set = dx_i may depend on x_r (conservative:
+ * all ones for anything but plain element statements).  The kernel skips sigma-point columns that cannot move a component. */
+int psy_drift_dependency(int n, const char* latent_equations, const psy_container* containers, int n_containers,
+                         unsigned* mask);
+
 /* ---- compileModel (R/prepareModel.R:553-562) ---------------------------------------------------------------
  * The reference writes model$cppCode to a temp file and hands it to Rcpp::sourceCpp (host g++).  Here the
  * generated CUDA translation unit (user drift + measurement statements spliced into the filter kernel template,

@@ -26,11 +26,26 @@ c_int_p = C.POINTER(C.c_int)
 c_int64_p = C.POINTER(C.c_int64)
 c_ubyte_p = C.POINTER(C.c_ubyte)
 
+
+class psy_container(C.Structure):
+    """include/psydiff_b200.h: one entry of model$pars$parameterList as the code generator sees it."""
+    _fields_ = [("name", C.c_char_p), ("is_scalar", C.c_int), ("rows", C.c_int), ("cols", C.c_int),
+                ("values", c_double_p), ("slots", c_int_p)]
+
+
+c_container_p = C.POINTER(psy_container)
+c_size_p = C.POINTER(C.c_size_t)
+c_uint_p = C.POINTER(C.c_uint)
+
 # name -> (restype, argtypes); kept in one table so tests can check every symbol of include/psydiff_b200.h
 SIGNATURES = {
     "psy_last_error": (C.c_char_p, []),
     "psy_version": (C.c_int, []),
     "psy_rk4_step_count": (C.c_int, [C.c_double, C.c_double]),
+    "psy_emit_model_source": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, c_container_p, C.c_int, C.c_int, C.c_int,
+                                        C.c_char_p, C.c_size_t, c_size_p]),
+    "psy_model_template": (C.c_int, [C.c_int, C.c_char_p, C.c_size_t, c_size_p]),
+    "psy_drift_dependency": (C.c_int, [C.c_int, C.c_char_p, c_container_p, C.c_int, c_uint_p]),
     "psy_model_compile": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
     "psy_model_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_char_p]),
     "psy_model_destroy": (None, [C.c_void_p]),

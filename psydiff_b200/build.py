@@ -6,7 +6,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 NVCC = os.environ.get("PSY_NVCC", "/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc")
-SOURCES = ["psy_capi.cu", "psy_primitives.cpp"]
+SOURCES = ["psy_capi.cu", "psy_primitives.cpp", "psy_codegen.cpp"]
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC,-pthread"]
 
 

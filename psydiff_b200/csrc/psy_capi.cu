@@ -119,6 +119,9 @@ struct Chunk { int theta; int start; int len; int pad; };
 
 }  // namespace
 
+// error reporting for the other translation units of the library (psy_codegen.cpp)
+int psy_set_error(int code, const char* msg) { return fail(code, "%s", msg); }
+
 // host-only bookkeeping of one finite-difference sweep (the eps[] fallback of R/modelTemplate.R:885-898, 905-919)
 struct psy_sweep {
   int P = 0;

@@ -1,7 +1,29 @@
 # psydiff_b200.R — R side of the drop-in: same function names and return values as the reference
 # (compileModel R/prepareModel.R:553-562; fitModel / getGradients / getGradient R/modelTemplate.R:165-166, 853-854, 932-933;
-# getGradientsParallel R/prepareModel.R:608-616).  newPsydiff is unchanged except that model$cppCode is produced by the
-# CUDA code generator (a port of psydiff_b200/codegen.py) instead of modelTemplate().
+# getGradientsParallel R/prepareModel.R:608-616).  newPsydiff is unchanged except that model$cppCode is produced by
+# psydiffCudaSource() below — the library's own code generator (psy_emit_model_source, psy_codegen.cpp) — instead of
+# pasting prepareEquations() into modelTemplate() (R/prepareModel.R:479-512):
+#
+#   modelCpp <- psydiffCudaSource(nlatent, nmanifest, latentEquations, manifestEquations, parameterList,
+#                                 parameterTableInit, srUpdate, integrateFunction)
+
+# parameterList: named list of start values (numeric scalars / matrices), parameterTableInit: one person's rows of the
+# parameter table (label, value, target, targetClass, row, col; row/col 0-based as extractParameters writes them,
+# R/prepareModel.R:646-690).  The k-th row of parameterTableInit is free slot k-1 of every filter instance.
+psydiffCudaSource <- function(nlatent, nmanifest, latentEquations, manifestEquations, parameterList, parameterTableInit,
+                              srUpdate = TRUE, integrateFunction = "default") {
+  values <- lapply(parameterList, function(v) { v <- as.matrix(v); storage.mode(v) <- "double"; v })
+  slots <- lapply(values, function(v) matrix(-1L, nrow(v), ncol(v)))
+  for (k in seq_len(nrow(parameterTableInit))) {
+    tg <- as.character(parameterTableInit$target[k])
+    slots[[tg]][parameterTableInit$row[k] + 1L, parameterTableInit$col[k] + 1L] <- k - 1L
+  }
+  isScalar <- vapply(parameterList, function(v) is.null(dim(v)) && length(v) == 1L, logical(1))
+  .Call("R_psy_emit_source", as.integer(nlatent), as.integer(nmanifest), nrow(parameterTableInit),
+        paste(latentEquations, collapse = "\n"), paste(manifestEquations, collapse = "\n"),
+        names(parameterList), isScalar, values, slots, isTRUE(srUpdate),
+        if (identical(integrateFunction, "runge_kutta_dopri5")) 1L else 0L)
+}
 
 .psy_stepper <- function(f) switch(f, "rk4" = 0L, "runge_kutta_dopri5" = 1L, 2L)
 .psy_direction <- function(d) {

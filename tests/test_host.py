@@ -242,7 +242,7 @@ def test_drift_jacobian_sparsity_is_conservative():
 def test_r_shim_only_uses_declared_abi():
     """r/psydiff_b200_shim.c (compiled by an R maintainer, not here): every psy_* it calls is declared in the header."""
     hdr = open(os.path.join(ROOT, "include", "psydiff_b200.h")).read()
-    declared = set(re.findall(r"\b(psy_[A-Za-z0-9_]+)\s*\(", hdr)) | {"psy_model"}
+    declared = set(re.findall(r"\b(psy_[A-Za-z0-9_]+)\s*\(", hdr)) | {"psy_model", "psy_container"}
     shim = open(os.path.join(ROOT, "r", "psydiff_b200_shim.c")).read()
     used = set(re.findall(r"\b(psy_[A-Za-z0-9_]+)\b", shim))
     assert used - declared == set(), used - declared
@@ -425,3 +425,62 @@ def test_model_template_and_helpers():
     assert out[0, 0] == "a = -0.3" and out[0, 1] == "0.0" and out[1, 1] == "c = -0.5"
     s = pd.sepNameFromValue(out)
     assert s["labels"][1, 0] == "b" and s["values"][1, 0] == 0.2
+
+
+# ---- the C++ code generator behind the C ABI (psy_emit_model_source, psy_codegen.cpp) -------------------------------------
+def test_cpp_code_generator_equals_the_python_one_on_many_models():
+    """newPsydiff's source assembly lives in the shared library (callable from R and Python alike); the Python generator kept
+    in codegen.py is its cross-check: identical text for the BASELINE configs and 60 random model structures."""
+    from test_kernel_fuzz import random_model
+    kws = [synth.config_c1(N=3, T=4), synth.config_c1(N=3, T=4, srUpdate=False), synth.config_c3(N=3, T=4), synth.config_c4(N=3, T=4),
+           synth.config_coupled(K=4, N=3, T=4), synth.config_coupled(K=5, N=3, T=4)]
+    kws += [random_model(7000 + s, stepper=("rk4", "runge_kutta_dopri5")[s % 2], srUpdate=(s % 3 != 0))[0] for s in range(60)]
+    for kw in kws:
+        m = pd.newPsydiff(**kw)
+        spec = m["_spec"]
+        assert m["cppCode"] == codegen.emit_cuda(spec) == codegen.emit_cuda_py(spec)
+        assert codegen.drift_dependency(spec) == codegen.drift_dependency_py(spec)
+    assert codegen.modelTemplate(True).startswith("// generated by psydiff_b200.codegen")
+    L = _lib.lib()
+    need = C.c_size_t(0)
+    for sr in (0, 1):
+        assert L.psy_model_template(sr, None, 0, C.byref(need)) == 0
+        buf = C.create_string_buffer(need.value)
+        assert L.psy_model_template(sr, buf, need.value, None) == 0 and buf.value.decode() == codegen.modelTemplate(bool(sr))
+
+
+def test_cpp_code_generator_literals_round_trip_like_repr():
+    """Fixed values become C++ literals that read back bit for bit (shortest round-trip digits, Python-repr layout)."""
+    import copy
+    rng = np.random.default_rng(0)
+    vals = [0.0, -0.0, 1.0, -1.0, 1e-4, 1e-5, 9.999e-5, 123456789012345678.0, 1e15, 1e16, 1e17, 0.1, 1 / 3, 2.5e-300,
+            1.7976931348623157e308, 5e-324, 100.0, 1234.5, 1e22, 1e23, float("nan"), float("inf"), float("-inf")]
+    vals += list(rng.standard_normal(300) * 10.0 ** rng.integers(-30, 30, 300))
+    spec0 = pd.newPsydiff(**synth.config_c1(N=3, T=4))["_spec"]
+    for v in vals:
+        sp = copy.deepcopy(spec0)
+        c = sp.container("m0")
+        c.values[0, 0], c.slots[0, 0] = v, -1
+        src = codegen.emit_cuda(sp)
+        assert src == codegen.emit_cuda_py(sp)
+        text = [l for l in src.splitlines() if l.strip().startswith("m0[0] =")][0].split("=")[1].strip(" ;")
+        if np.isfinite(v):
+            assert float(text) == v and np.signbit(float(text)) == np.signbit(v)
+
+
+def test_cpp_code_generator_errors():
+    L = _lib.lib()
+    m = pd.newPsydiff(**synth.config_c1(N=3, T=4))
+    spec = m["_spec"]
+    arr, keep = codegen._c_containers(spec)
+    args = lambda **o: (o.get("n", 2), 2, spec.n_slots, spec.latentEquations.encode(), spec.manifestEquations.encode(), arr,
+                        o.get("nc", len(spec.containers)), 1, o.get("stepper", 0))
+    need = C.c_size_t(0)
+    assert L.psy_emit_model_source(*args(), None, 0, C.byref(need)) == 0 and need.value == len(m["cppCode"].encode()) + 1
+    small = C.create_string_buffer(16)
+    assert L.psy_emit_model_source(*args(), small, 16, None) == 1 and b"too small" in L.psy_last_error()
+    assert L.psy_emit_model_source(*args(n=3), None, 0, C.byref(need)) == 1 and b"nlatent x nlatent" in L.psy_last_error()
+    assert L.psy_emit_model_source(*args(stepper=2), None, 0, C.byref(need)) == 1 and b"stepper" in L.psy_last_error()
+    assert L.psy_emit_model_source(*args(nc=1), None, 0, C.byref(need)) == 1 and b"must include A0LogChol" in L.psy_last_error()
+    with pytest.raises(ValueError, match="lower triangular"):          # the Python front end turns the C error into ValueError
+        pd.newPsydiff(**synth.config_c1(N=3, T=4, A0=np.array([[1.0, 0.3], [0.0, 1.0]])))
