@@ -103,7 +103,11 @@ def build_shard(args, rank):
     from psydiff_b200 import synth
     npg = args.persons_per_gpu
     kw = synth.config_c4(N=npg, T=args.timepoints, seed=20210132 + rank, id_offset=rank * npg)
-    return pd.newPsydiff(**kw)
+    model = pd.newPsydiff(**kw)
+    # the host copy of the dataset in R's own layout (column-major, what model$data$observations is and what psy_upload
+    # takes): the end-to-end leg starts from this buffer, not from a row-major array it would first have to transpose
+    model["data"]["observations"] = np.asfortranarray(model["data"]["observations"])
+    return model
 
 
 def cpu_sample(args, model, steps=1, warmup=0):
