@@ -1,8 +1,9 @@
 """Python driver of the CPU oracle (oracle/psy_oracle.cpp).  TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED — see the header of psy_oracle.cpp: the reference holds no golden vectors for this path and cannot be
-built here; the oracle is anchored on the exact linear Kalman filter, SR == covariance for linear h, and primitive
-identities (tests/test_oracle_*.py).
+PARITY STATUS — see the header of psy_oracle.cpp: the reference holds no golden vectors for this path; the oracle is pinned to
+the reference's OWN C++ compiled and run here against stand-in third-party headers (oracle/reference_build.py,
+tests/test_reference_build.py, tests/golden/*_reference.json) and further anchored on the exact linear Kalman filter,
+SR == covariance for linear h, primitive identities, a numpy/LAPACK restatement and its own 80-bit build.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
 It takes the model object built by ``psydiff_b200.newPsydiff`` (the shared INPUT description: equations, containers,

@@ -4,14 +4,18 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it, and
 // only as the checker or as the timed CPU arm.
 //
-// PARITY UNPINNED: the reference (jhorzek/psydiff, R + Rcpp + RcppArmadillo + Boost.odeint) holds no golden
-// vectors for this path (inst/tinytest/test_psydiff.R:3-4 is `expect_equal(1 + 1, 2)`) and cannot be built
-// or run in this image (no R, Rcpp, Armadillo, Boost, LAPACK).  This file is a dependency-free restatement of
-// the reference's algorithm.  It is anchored instead on (i) the exact discrete-time Kalman filter for linear
-// models (tests/test_oracle_anchor.py), (ii) SR == covariance variant for linear measurement equations,
-// (iii) primitive identities.  Third-party arithmetic restated here: Boost.odeint (unpinned CRAN `BH`)
-// integrate_const<runge_kutta4> and integrate (controlled dopri5); Armadillo/LAPACK qr_econ, inv(trimatl),
-// inv, det, chol.
+// PARITY STATUS: the reference (jhorzek/psydiff, R + Rcpp + RcppArmadillo + Boost.odeint) holds no golden vectors for this
+// path (inst/tinytest/test_psydiff.R:3-4 is `expect_equal(1 + 1, 2)`) and cannot be built the way its authors build it
+// in this image (no R, Rcpp, Armadillo, Boost, LAPACK).  This file is a dependency-free restatement of the reference's
+// algorithm.  It is PINNED TO THE REFERENCE'S OWN C++ run here: oracle/reference_build.py compiles the fitModel /
+// getGradients text of R/modelTemplate.R and inst/include/psydiff*.h from /root/reference against stand-in headers for the
+// third-party interfaces only (oracle/refbuild/include) and tests/test_reference_build.py compares this file with it
+// (-2LL to 3e-14 on the linear model, 6e-12 on the nonlinear C4 model; states; gradients; every primitive); the same
+// outputs are committed as tests/golden/*_reference.json.  What stays a restatement — there and here — is third-party
+// arithmetic: Boost.odeint (unpinned CRAN `BH`) integrate_const<runge_kutta4> and integrate (controlled dopri5);
+// Armadillo/LAPACK qr_econ, inv(trimatl), inv, det, chol.  Further anchors: (i) the exact discrete-time
+// Kalman filter for linear models, (ii) SR == covariance variant for linear measurement equations, (iii) primitive
+// identities, (iv) a numpy/LAPACK restatement, (v) this file's own 80-bit build.
 //
 // Every function cites the reference file:line (relative to /root/reference) it follows.
 // Build: g++ -O2 -ffp-contract=off -shared -fPIC (see oracle/build.py).  All matrices column-major.

@@ -318,3 +318,22 @@ def test_edge_cases_single_row_all_missing_person_and_abi_errors():
     model["direction"] = "sideways"
     with pytest.raises(pd.PsydiffError, match="Unknown direction"):
         pd.getGradients(model)
+
+
+@pytest.mark.parametrize("name", ["c1", "c1_missing_cov", "c3", "c4", "n8"])
+def test_reference_run_fixtures(name):
+    """The CUDA path against the committed outputs of the REFERENCE'S OWN C++ (tests/golden/*_reference.json: fitModel /
+    getGradients of R/modelTemplate.R + inst/include/psydiff*.h, compiled and run by oracle/reference_build.py where
+    /root/reference exists).  -2LL and states within 1e-9; FD gradient within 1e-6 plus the double-precision FD noise floor."""
+    import json, os
+    import reference_fixtures as rf
+    ref = rf.load(name)
+    model = pd.newPsydiff(**rf.CASES[name]())
+    pd.compileModel(model)
+    assert model["pars"]["parameterTable"].theta_labels == ref["labels"]
+    rf.check_fit(pd.fitModel(model), ref, rtol=M2LL_RTOL)
+    if "getGradients" in ref:
+        exact = None
+        if name == "c4":
+            exact = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c4_oracle_ext.json")))["grad_clean"]
+        rf.check_gradient(np.array(list(pd.getGradients(model).values())), ref, exact=exact)

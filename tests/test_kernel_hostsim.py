@@ -181,3 +181,18 @@ def test_compile_time_variants_agree(flags):
         a = HostSim(model).fit()["m2LL"]
         b = HostSim(model, flags).fit()["m2LL"]
         assert np.max(np.abs(a - b) / np.abs(a)) < 1e-11
+
+
+@pytest.mark.parametrize("name", ["c1", "c1_missing_cov", "c3", "c4", "n8"])
+def test_kernel_source_equals_reference_run_fixtures(name):
+    """The kernel source (host-compiled) against the committed outputs of the reference's own C++ (oracle/_ref build)."""
+    import reference_fixtures as rf
+    ref = rf.load(name)
+    model = pd.newPsydiff(**rf.CASES[name]())
+    hs = HostSim(model)
+    rf.check_fit(hs.fit(), ref)
+    if "getGradients" in ref:
+        exact = None
+        if name == "c4":
+            exact = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c4_oracle_ext.json")))["grad_clean"]
+        rf.check_gradient(hs.gradients(eps=1e-6)["grad"], ref, exact=exact)

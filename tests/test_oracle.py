@@ -1,6 +1,8 @@
-"""The CPU oracle against its independent anchors (no GPU).  PARITY UNPINNED: the reference holds no golden vectors and
-cannot run here, so the oracle is pinned on (i) the exact discrete-time Kalman filter for linear models, (ii) SR ==
-covariance variant for linear measurement equations, (iii) primitive identities, (iv) its own 80-bit build."""
+"""The CPU oracle against its anchors (no GPU).  The reference holds no golden vectors; what pins the oracle is the reference's
+OWN C++ compiled and run here (tests/test_reference_build.py where /root/reference exists, and its committed outputs
+tests/golden/*_reference.json everywhere).  This file holds the independent anchors: (i) the exact discrete-time Kalman filter
+for linear models, (ii) SR == covariance variant for linear measurement equations, (iii) primitive identities, (iv) its own
+80-bit build, (v) a numpy/LAPACK restatement — and the comparison with the reference-run fixtures."""
 import ctypes as C
 import json
 import os
@@ -190,3 +192,23 @@ def test_cpp_oracle_vs_numpy_lapack_restatement():
         fc, latc = nr.fit_person_cov(obs[sl], dt[sl], drift, meas, None, p + 1, np.array([1.0, 0.5]), np.array(kw["A0"]),
                                      np.array(kw["L"]), np.array(kw["Rchol"]), h=0.05)
         assert abs(fc - refc["m2LL"][p]) / abs(fc) < 1e-11 and np.max(np.abs(latc - refc["latentScores"][sl])) < 1e-10
+
+
+# ---- the oracle against the committed outputs of the reference's own C++ (oracle/_ref build, tests/golden/*_reference.json) ----
+@pytest.mark.parametrize("name", ["c1", "c1_missing_cov", "c3", "c4", "n8"])
+def test_oracle_equals_reference_run_fixtures(name):
+    import json
+    import reference_fixtures as rf
+    ref = rf.load(name)
+    model = pd.newPsydiff(**rf.CASES[name]())
+    assert model["pars"]["parameterTable"].theta_labels == ref["labels"]
+    o = Oracle(model)
+    rel = rf.check_fit(o.fit(), ref)
+    if name == "c1":
+        assert rel < 1e-12
+    if "getGradients" in ref:
+        g = o.gradients(nthreads=8)
+        exact = None
+        if name == "c4":
+            exact = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c4_oracle_ext.json")))["grad_clean"]
+        rf.check_gradient(g["grad_ref"], ref, exact=exact)

@@ -1,0 +1,299 @@
+"""The oracle against the REFERENCE'S OWN C++ run here (oracle/reference_build.py -> oracle/_ref): the fitModel / getGradients
+/ getGradient text of R/modelTemplate.R with the model's equations spliced in, and inst/include/psydiffBasic.h /
+psydiffInternals.h, compiled from /root/reference against stand-in Rcpp / Armadillo / Boost.odeint headers.  This is what pins the
+oracle: the loops, the parameter plumbing, every primitive and the finite-difference bookkeeping below are the reference
+authors' code, not a restatement.  Skipped where /root/reference is absent (the GPU box): there the committed fixtures
+tests/golden/*_reference.json, written from this build by tests/golden/make_golden.py, carry the same numbers.
+"""
+import numpy as np
+import pytest
+
+import psydiff_b200 as pd
+from psydiff_b200 import _lib, synth, primitives as prim
+from oracle import reference_build as rb
+
+pytestmark = pytest.mark.skipif(not rb.available(), reason="reference sources not present on this machine")
+
+M2LL_RTOL = 1e-9
+
+
+def _oracle(model, extended=False):
+    from oracle.oracle import Oracle
+    return Oracle(model, extended=extended)
+
+
+def _fit_pair(model, skip_update=False):
+    ref = rb.Reference(model).fit(skip_update=skip_update)
+    orc = _oracle(model).fit(skip_update=skip_update)
+    assert np.array_equal(np.isfinite(ref["m2LL"]), np.isfinite(orc["m2LL"]))
+    fin = np.isfinite(ref["m2LL"])
+    rel = np.abs(orc["m2LL"][fin] - ref["m2LL"][fin]) / np.maximum(np.abs(ref["m2LL"][fin]), 1e-300)
+    assert rel.max() < M2LL_RTOL, rel.max()
+    scale = max(1.0, np.nanmax(np.abs(ref["latentScores"])))
+    assert np.nanmax(np.abs(orc["latentScores"] - ref["latentScores"])) < 1e-9 * scale
+    assert np.nanmax(np.abs(orc["predictedManifest"] - ref["predictedManifest"])) < 1e-9 * scale
+    assert not ref["changed"].any()                       # fitModel clears the flags by reference (R/modelTemplate.R:410)
+    return ref, orc, rel.max()
+
+
+def _grad_pair(model):
+    """getGradients of the reference vs the oracle's literal reproduction of its bookkeeping (grad_ref), to the rounding floor of
+    a finite difference of Σ-2LL in double precision."""
+    g = rb.Reference(model).gradients()
+    og = _oracle(model).gradients(nthreads=8)
+    assert list(g) == model["pars"]["parameterTable"].theta_labels          # named, getParameterValues order
+    gv = np.array(list(g.values()))
+    assert np.array_equal(np.isfinite(gv), np.isfinite(og["grad_ref"]))
+    eps = float(np.atleast_1d(model["eps"])[0])
+    atol = 64 * np.finfo(float).eps * abs(float(np.nansum(og["m2LL"]))) / (2 * eps)
+    fin = np.isfinite(gv)
+    return gv, og, np.abs(gv[fin] - og["grad_ref"][fin]), atol
+
+
+def test_c1_fit_states_and_gradient():
+    model = pd.newPsydiff(**synth.config_c1())
+    _, _, rel = _fit_pair(model)
+    assert rel < 1e-12                                    # linear model: the two agree to rounding
+    gv, og, err, atol = _grad_pair(model)
+    assert np.all(err <= 1e-6 * np.abs(og["grad_ref"]) + atol)
+
+
+def test_missing_ragged_and_unobserved_person():
+    kw = synth.config_c1(N=12, T=14, missing=0.25, seed=7)
+    obs = kw["dataset"]["observations"]
+    obs[5] = np.nan
+    keep = np.ones(len(obs), dtype=bool)
+    keep[3 * 14 + 9:4 * 14] = False                      # a shorter person
+    keep[7 * 14 + 1:8 * 14] = False                      # a single-row person (dt = 0: no integration)
+    obs[9 * 14:10 * 14] = np.nan                          # nothing observed
+    for k in ("person", "observations", "dt"):
+        kw["dataset"][k] = kw["dataset"][k][keep]
+    ref, _, _ = _fit_pair(pd.newPsydiff(**kw))
+    assert ref["m2LL"][9] == 0.0
+
+
+def test_skip_update():
+    ref, orc, _ = _fit_pair(pd.newPsydiff(**synth.config_c1(N=5, T=9)), skip_update=True)
+    assert np.all(ref["m2LL"] == 0.0)
+
+
+def test_irregular_dt():
+    kw = synth.config_c1(N=8, T=15, seed=11)
+    rng = np.random.default_rng(5)
+    dt = rng.choice([0.01, 0.2, 0.5, 0.77, 1.0, 1.31], size=8 * 15)
+    dt[::15] = 0.0
+    kw["dataset"]["dt"] = dt
+    kw["timeStep"] = np.array([1.0 / 30])
+    _fit_pair(pd.newPsydiff(**kw))
+
+
+def test_covariance_variant():
+    model = pd.newPsydiff(**synth.config_c1(N=8, T=12, missing=0.2, seed=9, srUpdate=False))
+    _fit_pair(model)
+    _fit_pair(pd.newPsydiff(**synth.config_c4(N=3, T=6, srUpdate=False)))
+
+
+def test_dopri5():
+    _fit_pair(pd.newPsydiff(**synth.config_c1(N=6, T=10, integrateFunction="runge_kutta_dopri5")))
+    _fit_pair(pd.newPsydiff(**synth.config_c3(N=6, T=10)))             # Van der Pol, mu | person
+
+
+def test_c4_nonlinear_grouped_irregular():
+    model = pd.newPsydiff(**synth.config_c4(N=4, T=6))
+    ref, orc, rel = _fit_pair(model)
+    # both are double-precision evaluations of the same formulation; the 80-bit build of the oracle says how far each is from
+    # the exact value of that formulation
+    ext = _oracle(model, extended=True).fit()["m2LL"]
+    assert np.max(np.abs(ref["m2LL"] - ext) / np.abs(ext)) < 1e-9
+    gv, og, err, atol = _grad_pair(model)
+    # at eps = 1e-6 the double-precision FD gradient of this model carries ~1e-4 relative rounding noise: the
+    # reference and the oracle agree within that noise, and both sit within it of the 80-bit gradient
+    g80 = _oracle(model, extended=True).gradients(nthreads=8)["grad_clean"]
+    noise = np.max(np.abs(og["grad_ref"] - g80))
+    assert np.max(np.abs(gv - g80)) < 20 * max(noise, atol)
+
+
+@pytest.mark.parametrize("K", [4, 5])
+def test_n8_n10(K):
+    _fit_pair(pd.newPsydiff(**synth.config_coupled(K=K, N=3, T=5, n_groups=2)))
+
+
+def test_nonlinear_measurement_quirk_q3():
+    """With a nonlinear h the column-0 deviation is non-zero, so the v^(1/4)-weighted up/down-date of predictSquareRootOfS_C
+    (psydiffInternals.h:151-152, 187-195) matters: the oracle reproduces it literally."""
+    rng = np.random.default_rng(4)
+    N, T = 6, 12
+    obs = 1.0 + rng.standard_normal((N * T, 2))
+    obs[rng.random(obs.shape) < 0.1] = np.nan
+    kw = dict(dataset={"person": np.repeat(np.arange(1, N + 1), T), "observations": obs, "dt": np.tile(np.r_[0.0, np.full(T - 1, 1.0)], N)},
+              latentEquations="dx(0) = -0.4*x(0) + c1*x(1);\ndx(1) = -0.3*x(1);",
+              manifestEquations="y(0) = x(0) + q*x(0)*x(0);\ny(1) = exp(0.3*x(1));", parameters={"c1": 0.2, "q": 0.15},
+              L=np.diag([0.5, 0.4]), Rchol=np.diag([0.6, 0.5]), A0=np.diag([0.8, 0.7]), m0=np.array([[1.0], [0.5]]),
+              integrateFunction="rk4", eps=np.array([1e-6]))
+    for alpha in (0.2, 0.81):                              # negative and positive wc0: "downdate" and "update" branches
+        _fit_pair(pd.newPsydiff(**dict(kw, alpha=alpha)))
+
+
+def test_time_conventions_matrix_containers_and_full_L_R():
+    """Drift sees interval-local time, the measurement equation absolute time; matrix containers, whole-vector statements, %,
+    lower-triangular L and Rchol."""
+    rng = np.random.default_rng(5)
+    N, T = 5, 10
+    obs = 0.5 + rng.standard_normal((N * T, 2))
+    kw = dict(
+        dataset={"person": np.repeat(np.arange(1, N + 1), T), "observations": obs, "dt": np.tile(np.r_[0.0, np.full(T - 1, 0.7)], N)},
+        latentEquations="dx = DRIFT*x + CINT;\ndx(1) = dx(1) - 0.1*x(1)*x(1)*x(1) + 0.3*t;\ndx = dx - 0.01*(x % x);",
+        manifestEquations="y = LAMBDA*x;\ny = y + MANIFESTMEANS;\ny(0) = y(0) + 0.2*sin(0.5*t);",
+        parameters={"DRIFT": np.array([["d11 = -0.5", "0.1"], ["d21 = 0.2", "d22 = -0.6"]], dtype=object),
+                    "CINT": np.array([["c1 = 0.3"], ["0.1"]], dtype=object),
+                    "LAMBDA": np.array([["1", "0"], ["l21 = 0.4", "1"]], dtype=object),
+                    "MANIFESTMEANS": np.array([["0.2"], ["mm2 = -0.1"]], dtype=object)},
+        L=np.array([["l1 = 0.5", "0"], ["l21x = 0.1", "l2 = 0.4"]], dtype=object),
+        Rchol=np.array([["r1 = 0.6", "0"], ["r21 = 0.1", "r2 = 0.5"]], dtype=object),
+        A0=np.array([["0.8", "0"], ["a21 = 0.1", "0.7"]], dtype=object), m0=np.array([[1.0], [0.5]]),
+        integrateFunction="rk4", eps=np.array([1e-6]))
+    _fit_pair(pd.newPsydiff(**kw))
+    _fit_pair(pd.newPsydiff(**dict(kw, integrateFunction="runge_kutta_dopri5")))
+    _fit_pair(pd.newPsydiff(**dict(kw, srUpdate=False)))
+
+
+def test_failing_person_and_break_early():
+    """Quirk Q2: a person whose filter fails gets NaN.  With breakEarly = FALSE the reference evaluates everybody — the oracle's
+    (and the kernel's) position; with the default breakEarly = TRUE it returns at the first failure and leaves later persons at 0."""
+    kw = synth.config_c1(N=6, T=10, breakEarly=False)
+    model = pd.newPsydiff(**kw)
+    pd.setParameterValues(model["pars"]["parameterTable"], {"drift_eta1": 400.0})
+    ref = rb.Reference(model).fit()
+    orc = _oracle(model).fit()
+    assert np.array_equal(np.isfinite(ref["m2LL"]), np.isfinite(orc["m2LL"])) and not np.isfinite(ref["m2LL"]).all()
+    model2 = pd.newPsydiff(**synth.config_c1(N=6, T=10))
+    pd.setParameterValues(model2["pars"]["parameterTable"], {"drift_eta1": 400.0})
+    early = rb.Reference(model2).fit()["m2LL"]
+    first_bad = int(np.flatnonzero(~np.isfinite(orc["m2LL"]))[0])
+    assert not np.isfinite(early[first_bad]) and np.all(early[first_bad + 1:] == 0.0)
+    assert np.isnan(np.sum(early)) == np.isnan(np.sum(orc["m2LL"]))      # what every caller looks at (anyNA / sum)
+
+
+def test_eps_fallback_and_the_nan_poisoning_quirk_q8():
+    """What running the reference's code shows about its eps[] fallback (R/modelTemplate.R:885-898, 905-919):
+    fitModel "resets" a person's -2LL and predictions by subtracting them from themselves (`m2LL.elem(i) -= m2LL.elem(i)`,
+    R/modelTemplate.R:255-261), and NaN - NaN is NaN.  So once one evaluation on a model object was non-finite, every later
+    evaluation on that object returns NaN for that person — in getGradients (which works on one clone for the whole sweep) every
+    entry after the first failing step is NaN, whatever eps[] still holds.  The oracle and the kernel are stateless (each
+    evaluation starts from zero): they implement the fallback the code intends.  Both facts are pinned here."""
+    kw = dict(N=6, T=20, A0=np.eye(2), breakEarly=False)
+    # (a) no failure anywhere: only the first eps is used, and the reference agrees with the oracle
+    model = pd.newPsydiff(**synth.config_c1(eps=np.array([1e-6, 1e-4]), **kw))
+    gv, og, err, atol = _grad_pair(model)
+    assert np.all(err <= 1e-6 * np.abs(og["grad_ref"]) + atol)
+    # (b) the +30 step on the first parameter (a drift diagonal) is non-finite: the reference poisons everything after it
+    model = pd.newPsydiff(**synth.config_c1(eps=np.array([30.0, 1e-6]), **kw))
+    R = rb.Reference(model)
+    th = np.array(model["pars"]["parameterTable"].theta_values)
+    up, down = th.copy(), th.copy()
+    up[1] += 30
+    down[1] -= 30
+    assert np.isfinite(R.fit(theta=up)["m2LL"]).all() and np.isfinite(R.fit(theta=down)["m2LL"]).all()   # parameter 1 is harmless
+    g = np.array(list(R.gradients().values()))
+    assert np.isnan(g).all()                               # ... yet its gradient entry is NaN in the reference, like all others
+    og = _oracle(model).gradients()
+    assert np.isfinite(og["grad_clean"]).all()             # stateless semantics: the second eps resolves the failing sides
+    one = _oracle(pd.newPsydiff(**synth.config_c1(eps=np.array([1e-6]), **kw))).gradients()["grad_clean"]
+    ok = [1, 2, 4, 5]                                      # parameters whose ±30 steps are finite: eps used = 30 + 30
+    bad = [0, 3, 6, 7]                                     # right step falls back to 1e-6: denominator 30 + 1e-6
+    assert np.all(np.abs(og["grad_clean"][bad]) < 1e-2 * np.abs(one[bad]) + 10)   # a 30-wide secant, not the local slope
+    assert len(ok) + len(bad) == len(one)
+
+
+def test_single_parameter_gradient():
+    model = pd.newPsydiff(**synth.config_c1(N=5, T=8))
+    R = rb.Reference(model)
+    g = np.array(list(R.gradients().values()))
+    for par in (0, 4, 10):
+        assert R.gradient(par) == pytest.approx(g[par], rel=1e-9, abs=1e-9)
+
+
+def _abi_predictSquareRootOfS(Y, mu, Rchol, w0, w1):
+    m, s = Y.shape
+    out = np.empty((m, m), order="F")
+    _lib.lib().psy_predictSquareRootOfS(m, s, _lib.dptr(np.asfortranarray(Y)), _lib.dptr(np.ascontiguousarray(mu)),
+                                        _lib.dptr(np.asfortranarray(Rchol)), float(w0), float(w1), _lib.dptr(out))
+    return np.ascontiguousarray(out)
+
+
+def _abi_computeK_SR(Cm, srS):
+    n, m = Cm.shape
+    out = np.empty((n, m), order="F")
+    assert _lib.lib().psy_computeK_SR(n, m, _lib.dptr(np.asfortranarray(Cm)), _lib.dptr(np.asfortranarray(srS)), _lib.dptr(out)) == 0
+    return np.ascontiguousarray(out)
+
+
+def _abi_m2ll_chol(k, raw, em, srS):
+    import ctypes as C
+    out = C.c_double(0)
+    assert _lib.lib().psy_computeIndividualM2LLChol(k, _lib.dptr(np.ascontiguousarray(raw)), _lib.dptr(np.ascontiguousarray(em)),
+                                                    _lib.dptr(np.asfortranarray(srS)), C.byref(out)) == 0
+    return out.value
+
+
+def test_primitives_of_the_c_abi_equal_the_reference_headers():
+    """psy_primitives.cpp (what R code calling getSigmaPoints(), cholupdate(), ... would reach) against the reference's own
+    inst/include/psydiffInternals.h functions on random inputs."""
+    R = rb.Reference(pd.newPsydiff(**synth.config_c1(N=3, T=4)))
+    rng = np.random.default_rng(2)
+    n, m = 4, 3
+    s = 2 * n + 1
+    alpha, beta, kappa = 0.2, 2.0, 0.0
+    c = alpha ** 2 * (n + kappa)
+    wm = R.primitive("getMeanWeights", scalars=(n, alpha, beta, kappa), out_shape=(s,))
+    wc = R.primitive("getCovWeights", scalars=(n, alpha, beta, kappa), out_shape=(s,))
+    assert np.array_equal(wm, prim.getMeanWeights(n, alpha, beta, kappa)) and np.array_equal(wc, prim.getCovWeights(n, alpha, beta, kappa))
+    W = R.primitive("getWMatrix", wm, wc, out_shape=(s, s))
+    assert np.allclose(W, prim.getWMatrix(wm, wc), rtol=1e-13, atol=1e-13)
+    A = np.tril(rng.standard_normal((n, n))) + 2 * np.eye(n)
+    mu = rng.standard_normal(n)
+    X = R.primitive("getSigmaPoints", mu, A, scalars=(1, c), out_shape=(n, s))
+    assert np.array_equal(X, prim.getSigmaPoints(mu, A, True, c))
+    X2 = R.primitive("getSigmaPoints", mu, A @ A.T, scalars=(0, c), out_shape=(n, s))
+    assert np.allclose(X2, prim.getSigmaPoints(mu, A @ A.T, False, c), rtol=1e-12, atol=1e-12)
+    assert np.allclose(R.primitive("getAFromSigmaPoints", X, wm, scalars=(c,), out_shape=(n, n)), prim.getAFromSigmaPoints(X, wm, c), rtol=1e-12, atol=1e-12)
+    assert np.allclose(R.primitive("computePFromSigmaPoints", X, wm, scalars=(c,), out_shape=(n, n)), prim.computePFromSigmaPoints(X, wm, c), rtol=1e-12, atol=1e-12)
+    Mx = rng.standard_normal((n, n))
+    assert np.array_equal(R.primitive("getPhi", Mx, out_shape=(n, n)), prim.getPhi(Mx))
+    Y = rng.standard_normal((m, s))
+    Rc = np.tril(rng.standard_normal((m, m)) * 0.2) + 0.6 * np.eye(m)
+    muY = np.asarray(prim.predictMu(Y, wm)).ravel()
+    assert np.allclose(R.primitive("predictMu", Y, wm, out_shape=(m,)), muY, rtol=1e-13, atol=1e-13)
+    for w0 in (wc[0], 0.7):                                # negative (downdate) and positive (update) covWeight_0
+        a = R.primitive("predictSquareRootOfS", Y, muY, Rc, scalars=(w0, wc[1]), out_shape=(m, m))
+        b = _abi_predictSquareRootOfS(Y, muY, Rc, w0, wc[1])
+        assert np.allclose(a, b, rtol=1e-11, atol=1e-12)
+    S = prim.predictS(Y, W, Rc @ Rc.T)
+    assert np.allclose(R.primitive("predictS", Y, W, Rc @ Rc.T, out_shape=(m, m)), S, rtol=1e-12, atol=1e-12)
+    Cm = prim.predictC(X, Y, W)
+    assert np.allclose(R.primitive("predictC", X, Y, W, out_shape=(n, m)), Cm, rtol=1e-12, atol=1e-12)
+    Sp = Rc @ Rc.T + np.eye(m)
+    assert np.allclose(R.primitive("computeK", Cm, Sp, out_shape=(n, m)), prim.computeK(Cm, Sp), rtol=1e-11, atol=1e-12)
+    Ls = np.linalg.cholesky(Sp)
+    assert np.allclose(R.primitive("computeK_SR", Cm, Ls, out_shape=(n, m)), _abi_computeK_SR(Cm, Ls), rtol=1e-11, atol=1e-12)
+    K = prim.computeK(Cm, Sp)
+    res = rng.standard_normal(m)
+    assert np.allclose(R.primitive("updateM", mu, K, res, out_shape=(n,)), np.asarray(prim.updateM(mu, K, res)).ravel(), rtol=1e-13, atol=1e-13)
+    P = A @ A.T
+    assert np.allclose(R.primitive("updateP", P, K, Sp, out_shape=(n, n)), prim.updateP(P, K, Sp), rtol=1e-12, atol=1e-12)
+    raw, em = rng.standard_normal(m), rng.standard_normal(m)
+    assert R.primitive("computeIndividualM2LL", raw, em, Sp, scalars=(m,))[0] == pytest.approx(prim.computeIndividualM2LL(m, raw, em, Sp), rel=1e-12)
+    assert R.primitive("computeIndividualM2LLChol", raw, em, Ls, scalars=(m,))[0] == pytest.approx(_abi_m2ll_chol(m, raw, em, Ls), rel=1e-12)
+    x = rng.standard_normal(n) * 0.3
+    Lc = np.linalg.cholesky(P)
+    for direction, v in (("update", 1.0), ("downdate", 1.0), ("update", 0.37)):
+        a = R.primitive("cholupdate", Lc, x, scalars=(v,), text=direction, out_shape=(n, n))
+        assert np.allclose(a, prim.cholupdate(Lc, x, v, direction), rtol=1e-12, atol=1e-13)
+    with pytest.raises(RuntimeError, match="Unknown direction in cholupdate"):
+        R.primitive("cholupdate", Lc, x, scalars=(1.0,), text="sideways", out_shape=(n, n))
+    T = rng.standard_normal((7, 3))
+    Rq = R.primitive("qr_", T, out_shape=(3, 3))
+    Rm = prim.qr_(T)
+    assert np.allclose(np.abs(Rq), np.abs(Rm), rtol=1e-12, atol=1e-13)     # R is unique up to row signs
+    lc = rng.standard_normal((n, n))
+    assert np.array_equal(R.primitive("logChol2Chol", lc, out_shape=(n, n)), prim.logChol2Chol(lc))
