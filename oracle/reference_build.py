@@ -17,7 +17,7 @@ into the repository; everything generated goes to oracle/_ref/, which is git-ign
 So the person loop, the time loop, the parameter plumbing (setParameterList_C and its `changed` flags), every filter primitive,
 the finite-difference bookkeeping and every quirk of the reference run as their authors wrote them; only LAPACK-level numerics
 (QR, triangular inverse, Cholesky, LU) and the ODE stepper are restatements.  tests/test_reference_build.py checks the oracle
-(oracle/psy_oracle.cpp) against it, and tests/golden/make_golden.py writes its outputs into the committed fixtures the GPU
+(oracle/psy_oracle.cpp) against it, and tests/golden/make_reference_golden.py writes its outputs into the committed fixtures the GPU
 tests read (the GPU box has no /root/reference).
 """
 from __future__ import annotations
@@ -88,10 +88,32 @@ def model_source(spec) -> str:
     return code + '\n#include "ref_driver.inc"\n'
 
 
+def _manifest_key(spec) -> str:
+    """Identifies a model without reading the reference: its equations, containers' shapes/kinds and update variant."""
+    desc = repr((spec.nlatent, spec.nmanifest, spec.latentEquations, spec.manifestEquations, bool(spec.srUpdate),
+                 [(c.name, c.kind, tuple(c.values.shape)) for c in spec.containers]))
+    return hashlib.sha1(desc.encode()).hexdigest()[:16]
+
+
+def prebuilt(spec):
+    """Path of the binary built earlier for this model (oracle/_ref/manifest.json), or None.  What the GPU box — which has the
+    prebuilt files but no /root/reference — uses."""
+    import json
+    mf = os.path.join(_OUT, "manifest.json")
+    if not os.path.exists(mf):
+        return None
+    so = json.load(open(mf)).get(_manifest_key(spec))
+    return os.path.join(_OUT, so) if so and os.path.exists(os.path.join(_OUT, so)) else None
+
+
 def build(spec) -> str:
-    """Compile the model's reference translation unit into oracle/_ref/ref_<hash>.so (g++ only; needs /root/reference)."""
+    """Compile the model's reference translation unit into oracle/_ref/ref_<hash>.so (g++ only; needs /root/reference; where it
+    is absent the binary recorded in oracle/_ref/manifest.json for this model is returned)."""
     if not available():
-        raise RuntimeError(f"reference sources not found under {REFERENCE}")
+        so = prebuilt(spec)
+        if so:
+            return so
+        raise RuntimeError(f"reference sources not found under {REFERENCE} and no prebuilt binary for this model in oracle/_ref")
     src = model_source(spec)
     deps = "".join(open(p).read() for p in (
         _DRIVER, os.path.join(_INC, "RcppArmadillo.h"), os.path.join(_INC, "boost", "numeric", "odeint.hpp"),
@@ -100,16 +122,20 @@ def build(spec) -> str:
     so = os.path.join(_OUT, f"ref_{key}.so")
     if not os.path.exists(so):
         os.makedirs(_OUT, exist_ok=True)
-        cpp = os.path.join(_OUT, f"ref_{key}.cpp")
-        with open(cpp, "w") as f:
-            f.write(src)
-        # -ffp-contract=off: the reference is built by R's default flags (-O2, no FMA contraction on x86-64)
+        # the assembled translation unit (reference text + spliced equations) is piped to the compiler, never written to disk:
+        # only the binary lands in oracle/_ref/.  -ffp-contract=off: R's default flags (-O2, no FMA contraction on x86-64)
         cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I", _INC,
-               "-I", os.path.join(REFERENCE, "inst", "include"), "-I", os.path.join(_HERE, "refbuild"), "-o", so + ".tmp", cpp]
-        r = subprocess.run(cmd, capture_output=True, text=True)
+               "-I", os.path.join(REFERENCE, "inst", "include"), "-I", os.path.join(_HERE, "refbuild"), "-o", so + ".tmp", "-x", "c++", "-"]
+        r = subprocess.run(cmd, input=src, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("reference translation unit does not compile against the stand-in headers:\n" + r.stderr[:6000])
         os.replace(so + ".tmp", so)
+    import json
+    mf = os.path.join(_OUT, "manifest.json")
+    man = json.load(open(mf)) if os.path.exists(mf) else {}
+    if man.get(_manifest_key(spec)) != os.path.basename(so):
+        man[_manifest_key(spec)] = os.path.basename(so)
+        json.dump(man, open(mf, "w"), indent=1)
     return so
 
 
