@@ -205,6 +205,32 @@ def test_eps_fallback_and_the_nan_poisoning_quirk_q8():
     assert len(ok) + len(bad) == len(one)
 
 
+def test_quirk_q4_shared_parameter_list_is_history_dependent():
+    """Quirk Q4, observed: setParameterList_C copies only a person's CHANGED rows into a parameter list shared by all persons
+    (psydiffBasic.h:95).  The first fit (all flags TRUE) is right and equals the oracle.  In the gradient sweep that follows, a
+    step on a COMMON parameter re-fits every person with only that row copied, so all persons run with the LAST person's
+    person-specific values: the reference's gradient entries of common parameters are off by O(1), those of the person-specific
+    parameters are right.  The oracle and the kernel use each person's own values throughout (stateless semantics)."""
+    model = pd.newPsydiff(**synth.config_c3(N=4, T=8, integrateFunction="rk4"))
+    pt = model["pars"]["parameterTable"]
+    specific = [l for l in pt.theta_labels if l.startswith("mu_p")]
+    pd.setParameterValues(pt, {l: 0.5 + 0.3 * i for i, l in enumerate(specific)})
+    R, o = rb.Reference(model), _oracle(model)
+    a, b = R.fit()["m2LL"], o.fit()["m2LL"]
+    assert np.max(np.abs(a - b) / np.abs(b)) < M2LL_RTOL
+    g = R.gradients()
+    og = dict(zip(pt.theta_labels, o.gradients()["grad_clean"]))
+    for lab in specific:
+        assert g[lab] == pytest.approx(og[lab], rel=1e-5)
+    off = [abs(g[l] - og[l]) / abs(og[l]) for l in pt.theta_labels if l not in specific]
+    assert max(off) > 0.5 and min(off) > 0.05
+    # with equal person-specific values the history does not matter and everything agrees
+    pd.setParameterValues(pt, {l: 0.8 for l in specific})
+    g2 = rb.Reference(model).gradients()
+    o2 = dict(zip(pt.theta_labels, _oracle(model).gradients()["grad_clean"]))
+    assert all(g2[l] == pytest.approx(o2[l], rel=1e-4, abs=1e-4) for l in pt.theta_labels)
+
+
 def test_single_parameter_gradient():
     model = pd.newPsydiff(**synth.config_c1(N=5, T=8))
     R = rb.Reference(model)
