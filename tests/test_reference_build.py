@@ -323,3 +323,13 @@ def test_primitives_of_the_c_abi_equal_the_reference_headers():
     assert np.allclose(np.abs(Rq), np.abs(Rm), rtol=1e-12, atol=1e-13)     # R is unique up to row signs
     lc = rng.standard_normal((n, n))
     assert np.array_equal(R.primitive("logChol2Chol", lc, out_shape=(n, n)), prim.logChol2Chol(lc))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_model_structures(seed):
+    """Seeded random structures (tests/test_kernel_fuzz.py: n, m, sparse / dense drift, grouped parameters, t and person in the
+    equations, nonlinear measurement, diagonal / full L and Rchol, three alpha values, missing and ragged data, dt < h) through
+    the reference's own code and the oracle."""
+    from test_kernel_fuzz import random_model
+    kw, _ = random_model(9000 + seed, stepper=("rk4", "runge_kutta_dopri5")[seed % 2], srUpdate=(seed % 3 != 2))
+    _fit_pair(pd.newPsydiff(**dict(kw, breakEarly=False)))
