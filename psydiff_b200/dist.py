@@ -23,10 +23,46 @@ class _DevVec:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
 
 
-def shard_bounds(n_persons: int, world: int):
-    """Contiguous person blocks per rank (balanced by count; equal T and P_i make that balanced by work as well)."""
-    b = [(n_persons * r) // world for r in range(world + 1)]
+def shard_bounds(n_persons: int, world: int, work=None):
+    """Contiguous person blocks per rank.  Without ``work``: balanced by count (equal T and P_i make that balanced by work as
+    well — the benchmark configs).  With ``work`` (one non-negative number per person, e.g. ``person_work(model)``): the cut
+    points are placed where the running sum of work crosses r/world of the total, so ragged series, irregular dt and
+    person-specific parameters (different instance counts) still give every GPU the same share of filter steps."""
+    if work is None:
+        b = [(n_persons * r) // world for r in range(world + 1)]
+        return [(b[r], b[r + 1]) for r in range(world)]
+    w = np.asarray(work, dtype=np.float64)
+    if w.shape != (n_persons,) or np.any(w < 0) or not np.all(np.isfinite(w)):
+        raise ValueError("work must hold one finite non-negative number per person")
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    if cum[-1] <= 0:
+        return shard_bounds(n_persons, world)
+    b = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        k = int(np.searchsorted(cum, target, side="left"))          # first cut with cum >= target ...
+        if k > 0 and target - cum[k - 1] < cum[min(k, n_persons)] - target:
+            k -= 1                                                   # ... or the one before, whichever is closer
+        b.append(min(max(k, b[-1]), n_persons))
+    b.append(n_persons)
     return [(b[r], b[r + 1]) for r in range(world)]
+
+
+def person_work(psydiffModel) -> np.ndarray:
+    """Filter work of each person in one gradient evaluation: (2 P_i + 1) instances x Σ_t (K_t RK4 steps + 1 measurement update),
+    K_t by odeint's step rule (psy_rk4_step_count); P_i = number of distinct θ entries the person carries.  For dopri5 the step
+    count is data dependent; the rk4 count at the initial step size is used as the proxy."""
+    L = _lib.lib()
+    pt = psydiffModel["pars"]["parameterTable"]
+    dt = np.asarray(psydiffModel["data"]["dt"], dtype=np.float64)
+    h = float(np.atleast_1d(psydiffModel["timeStep"])[0])
+    udt, inv = np.unique(dt, return_inverse=True)
+    ksteps = np.array([L.psy_rk4_step_count(float(d), h) for d in udt], dtype=np.float64)[inv] + 1.0
+    off = np.asarray(psydiffModel["_row_off"], dtype=np.int64)
+    steps = np.add.reduceat(ksteps, off[:-1])
+    tidx = np.asarray(pt.theta_index)
+    distinct = np.array([len(np.unique(r)) for r in tidx]) if tidx.size else np.zeros(len(off) - 1)
+    return steps * (2.0 * distinct + 1.0)
 
 
 def allreduce_partial(partial_ptr: int, n: int, group=None) -> np.ndarray:

@@ -105,3 +105,36 @@ def test_merge_labels_first_appearance():
     labels, values, pos = pdist.merge_labels([["a", "b_p2"], ["a", "b_p1", "c"]], [[1.0, 2.0], [1.0, 3.0, 4.0]])
     assert labels == ["a", "b_p2", "b_p1", "c"] and list(values) == [1.0, 2.0, 3.0, 4.0] and pos["c"] == 3
     assert pdist.shard_bounds(10, 4) == [(0, 2), (2, 5), (5, 7), (7, 10)]
+
+
+def test_work_balanced_shard_bounds():
+    """contiguous person blocks balanced by work Σ_t K_t (2 P_i + 1), not by count."""
+    rng = np.random.default_rng(0)
+    # ragged persons with irregular dt: work differs by person
+    kw = synth.config_c1(N=40, T=30, seed=3)
+    keep = np.ones(40 * 30, dtype=bool)
+    for p in range(0, 40, 3):
+        keep[p * 30 + 8:(p + 1) * 30] = False              # every third person has 8 instead of 30 time points
+    d = {k: v[keep] for k, v in kw["dataset"].items()}
+    d["dt"] = np.where(d["dt"] > 0, rng.choice([0.5, 1.0, 2.0], size=len(d["dt"])), 0.0)
+    kw["dataset"] = d
+    model = pd.newPsydiff(**kw)
+    w = pdist.person_work(model)
+    assert w.shape == (40,) and np.all(w > 0)
+    # a person's work = (2 P + 1) x Σ_t (K_t + 1)
+    L = pd._lib.lib()
+    h = float(model["timeStep"][0])
+    off = model["_row_off"]
+    want0 = (2 * 11 + 1) * sum(L.psy_rk4_step_count(float(x), h) + 1 for x in d["dt"][off[0]:off[1]])
+    assert w[0] == want0
+    for world in (2, 3, 8):
+        b = pdist.shard_bounds(40, world, work=w)
+        assert b[0][0] == 0 and b[-1][1] == 40 and all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+        shares = np.array([w[lo:hi].sum() for lo, hi in b]) / w.sum()
+        by_count = np.array([w[lo:hi].sum() for lo, hi in pdist.shard_bounds(40, world)]) / w.sum()
+        assert np.max(np.abs(shares - 1 / world)) <= np.max(w) / w.sum() + 1e-12          # within one person of the ideal cut
+        assert np.max(np.abs(shares - 1 / world)) <= np.max(np.abs(by_count - 1 / world)) + 1e-12
+    assert pdist.shard_bounds(8, 4, work=np.ones(8)) == [(0, 2), (2, 4), (4, 6), (6, 8)]
+    assert pdist.shard_bounds(5, 2, work=np.zeros(5)) == pdist.shard_bounds(5, 2)
+    with pytest.raises(ValueError):
+        pdist.shard_bounds(5, 2, work=np.ones(4))
