@@ -325,7 +325,9 @@ def GIST(model, startingValues: Dict[str, float], lambda_, adaptiveLassoWeights:
         accepted = False
         while k < maxIter_in and not accepted:
             nb = max(1, min(int(batch), maxIter_in - k))
-            steps = [stepsize * eta ** i for i in range(nb)]
+            steps = [stepsize]
+            for _ in range(nb - 1):
+                steps.append(steps[-1] * eta)       # repeated multiplication, bit for bit the sequential loop's s, s*eta, (s*eta)*eta, ...
             cands = [proximal(st) for st in steps]
             if nb == 1:
                 fits = [fit_at(cands[0])]
