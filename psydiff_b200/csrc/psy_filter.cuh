@@ -62,19 +62,11 @@ __device__ __forceinline__ double rcp(double x) {
 #else
   r = psy_sim_rcp_seed(x);  // host compile of this header = tests/hostsim (kernel-source emulation in the CPU test suite)
 #endif
-#ifdef PSY_RCP_CUBIC
-  // one cubic step instead of two Newton steps: r (1 + e + e²), e = 1 − x r.  The seed is good to >= 20 bits, so the result
-  // is good to >= 60: 3 dependent FMAs instead of 4.  (Prepared experiment, not measured on the device yet: off by default.)
-  const double e = fma(-x, r, 1.0);
-  const double e2 = fma(e, e, e);
-  return fma(r, e2, r);
-#else
   double e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   return r;
-#endif
 #endif
 }
 

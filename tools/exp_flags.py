@@ -5,7 +5,7 @@ import numpy as np
 import psydiff_b200 as pd
 from psydiff_b200 import synth, _lib
 L = _lib.lib()
-variants = sys.argv[1:] or ["", "-DPSY_RCP_CUBIC"]
+variants = sys.argv[1:] or ["", "-DPSY_IEEE_DIV"]
 for name, kw, N in (("C4", synth.config_c4(N=8192, T=100), 8192), ("n8", synth.config_coupled(K=4, N=2048, T=100), 2048)):
     ref = None
     for v in variants + variants[:1]:                      # the first variant again at the end: drift check
