@@ -8,7 +8,7 @@ including the data to every worker on every call (R/prepareModel.R:608-616).  Pe
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Optional
+from typing import Dict
 
 import numpy as np
 

@@ -1,5 +1,5 @@
 """GPU experiment: kernel time of compile-flag variants on C4 (8192 persons) and the n = 8 model (2048 persons); min of 3 calls."""
-import sys, ctypes as C
+import sys
 sys.path.insert(0, '/root/repo')
 import numpy as np
 import psydiff_b200 as pd

@@ -1,9 +1,9 @@
 """Warm the in-tree cubin cache before a gpurun call: run every gpu-marked test on this (GPU-less) machine with newPsydiff
 patched to compile the model at once; each test then stops at the first device call.  The cubins travel with the snapshot, so
 the GPU box does not spend its minutes in nvcc.  (Models a test builds after its first device call are compiled on the box.)"""
-import sys, os, time, inspect, importlib, itertools
+import sys, os, time, inspect, importlib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
-import pytest, numpy as np
+
 import psydiff_b200 as pd
 from psydiff_b200 import model as M
 seen = {}
