@@ -212,3 +212,28 @@ def test_oracle_equals_reference_run_fixtures(name):
         if name == "c4":
             exact = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c4_oracle_ext.json")))["grad_clean"]
         rf.check_gradient(g["grad_ref"], ref, exact=exact)
+
+
+def test_dormand_prince_tableau_equals_scipys_in_all_three_implementations():
+    """The Dormand-Prince 5(4) coefficients of the kernel (psy_filter.cuh), the oracle (psy_oracle.cpp) and the odeint stand-in
+    of the reference build (oracle/refbuild) against an independent transcription: scipy.integrate's RK45 tableau."""
+    import re
+    from scipy.integrate._ivp.rk import RK45
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    want = {"a21": RK45.A[1][0], "a31": RK45.A[2][0], "a32": RK45.A[2][1], "a41": RK45.A[3][0], "a42": RK45.A[3][1], "a43": RK45.A[3][2],
+            "a51": RK45.A[4][0], "a52": RK45.A[4][1], "a53": RK45.A[4][2], "a54": RK45.A[4][3],
+            "a61": RK45.A[5][0], "a62": RK45.A[5][1], "a63": RK45.A[5][2], "a64": RK45.A[5][3], "a65": RK45.A[5][4],
+            "c1": RK45.B[0], "c3": RK45.B[2], "c4": RK45.B[3], "c5": RK45.B[4], "c6": RK45.B[5]}
+    err = {1: RK45.E[0], 3: RK45.E[2], 4: RK45.E[3], 5: RK45.E[4], 6: RK45.E[5], 7: RK45.E[6]}     # scipy: 5th minus 4th order weights, negated
+    for path, eprefix in (("psydiff_b200/csrc/psy_filter.cuh", "e"), ("oracle/psy_oracle.cpp", "dc"),
+                          ("oracle/refbuild/include/boost/numeric/odeint.hpp", "dc")):
+        text = open(os.path.join(root, path)).read()
+        env = {}
+        for name, expr in re.findall(r"\b([ace]\d+|dc\d)\s*=\s*([-+0-9./ c()]+?)\s*[,;]", text):
+            if re.fullmatch(r"[-+0-9./ c()]+", expr) and name not in env:
+                env[name] = eval(expr, {}, env)            # plain rational arithmetic, later ones refer to c1..c6
+        for k, v in want.items():
+            assert env[k] == pytest.approx(v, rel=1e-15), (path, k)
+        for i, v in err.items():
+            assert abs(env[f"{eprefix}{i}"]) == pytest.approx(abs(v), rel=1e-12), (path, i)
+        assert np.sign(env[f"{eprefix}1"]) * np.sign(env[f"{eprefix}7"]) == np.sign(err[1]) * np.sign(err[7])
