@@ -45,6 +45,8 @@ def main():
     case("c4", "C4: 3 coupled Van der Pol (n=m=6), irregular dt, 8 groups, N=16, T=12, rk4 h=min(dt)/30, eps=1e-6 central, seed 20210132 "
          "(synth.config_c4(N=16, T=12)); note: the reference's double-precision FD gradient of this model carries ~1e-4 relative "
          "rounding noise (see c4_oracle_ext.json for the 80-bit value)", synth.config_c4(N=16, T=12))
+    case("c4_T100", "C4 at the benchmark's series length: N=8, T=100 (about 62 RK4 steps per interval, 99 intervals), fit only "
+         "(synth.config_c4(N=8, T=100))", synth.config_c4(N=8, T=100), grad=False)
     case("n8", "C5's model: 4 coupled Van der Pol (n=m=8), N=6, T=8, 2 groups (synth.config_coupled(K=4, N=6, T=8, n_groups=2))",
          synth.config_coupled(K=4, N=6, T=8, n_groups=2), grad=False)
 

@@ -14,6 +14,7 @@ CASES = {
     "c1_missing_cov": lambda: synth.config_c1(N=24, T=30, missing=0.2, seed=9, srUpdate=False),
     "c3": lambda: synth.config_c3(N=16, T=12),
     "c4": lambda: synth.config_c4(N=16, T=12),
+    "c4_T100": lambda: synth.config_c4(N=8, T=100),
     "n8": lambda: synth.config_coupled(K=4, N=6, T=8, n_groups=2),
 }
 

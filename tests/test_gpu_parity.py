@@ -320,7 +320,7 @@ def test_edge_cases_single_row_all_missing_person_and_abi_errors():
         pd.getGradients(model)
 
 
-@pytest.mark.parametrize("name", ["c1", "c1_missing_cov", "c3", "c4", "n8"])
+@pytest.mark.parametrize("name", ["c1", "c1_missing_cov", "c3", "c4", "c4_T100", "n8"])
 def test_reference_run_fixtures(name):
     """The CUDA path against the committed outputs of the REFERENCE'S OWN C++ (tests/golden/*_reference.json: fitModel /
     getGradients of R/modelTemplate.R + inst/include/psydiff*.h, compiled and run by oracle/reference_build.py where

@@ -183,7 +183,7 @@ def test_compile_time_variants_agree(flags):
         assert np.max(np.abs(a - b) / np.abs(a)) < 1e-11
 
 
-@pytest.mark.parametrize("name", ["c1", "c1_missing_cov", "c3", "c4", "n8"])
+@pytest.mark.parametrize("name", ["c1", "c1_missing_cov", "c3", "c4", "c4_T100", "n8"])
 def test_kernel_source_equals_reference_run_fixtures(name):
     """The kernel source (host-compiled) against the committed outputs of the reference's own C++ (oracle/_ref build)."""
     import reference_fixtures as rf

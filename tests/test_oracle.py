@@ -195,7 +195,7 @@ def test_cpp_oracle_vs_numpy_lapack_restatement():
 
 
 # ---- the oracle against the committed outputs of the reference's own C++ (oracle/_ref build, tests/golden/*_reference.json) ----
-@pytest.mark.parametrize("name", ["c1", "c1_missing_cov", "c3", "c4", "n8"])
+@pytest.mark.parametrize("name", ["c1", "c1_missing_cov", "c3", "c4", "c4_T100", "n8"])
 def test_oracle_equals_reference_run_fixtures(name):
     import json
     import reference_fixtures as rf
