@@ -182,6 +182,7 @@ inline Mat operator/(const Mat& a, double s) { Mat r = a; for (auto& x : r.mem) 
 inline Mat operator+(const Mat& a, double s) { Mat r = a; for (auto& x : r.mem) x += s; return r; }
 inline Mat operator-(const Mat& a) { return -1.0 * a; }
 inline Mat operator%(const Mat& a, const Mat& b) { a.same(b); Mat r = a; for (uword k = 0; k < r.n_elem; k++) r.mem[k] *= b.mem[k]; return r; }
+inline Mat operator/(const Mat& a, const Mat& b) { a.same(b); Mat r = a; for (uword k = 0; k < r.n_elem; k++) r.mem[k] /= b.mem[k]; return r; }
 inline Mat operator-(const Mat& a, double s) { return a + (-s); }
 inline Mat operator+(double s, const Mat& a) { return a + s; }
 inline uvec operator==(const Mat& a, double s) { uvec u; for (double x : a.mem) u.v.push_back(x == s ? 1 : 0); u.n_elem = u.v.size(); return u; }
@@ -191,6 +192,8 @@ inline Mat eye(uword r, uword c) { Mat m(r, c); for (uword i = 0; i < std::min(r
 inline Mat diagmat(const Mat& v) { Mat m(v.n_elem, v.n_elem); for (uword i = 0; i < v.n_elem; i++) m(i, i) = v.mem[i]; return m; }
 inline Mat log(const Mat& a) { Mat r = a; for (auto& x : r.mem) x = std::log(x); return r; }
 inline Mat exp(const Mat& a) { Mat r = a; for (auto& x : r.mem) x = std::exp(x); return r; }
+inline double accu(const Mat& a) { double s = 0.0; for (double x : a.mem) s += x; return s; }
+inline double dot(const Mat& a, const Mat& b) { if (a.n_elem != b.n_elem) throw std::logic_error("dot(): objects must have the same number of elements"); double s = 0.0; for (uword k = 0; k < a.n_elem; k++) s += a.mem[k] * b.mem[k]; return s; }
 inline double sum(const Mat& a) { double s = 0.0; for (double x : a.mem) s += x; return s; }  // vectors only (all the reference uses)
 inline bool is_finite(const Mat& a) { for (double x : a.mem) if (!std::isfinite(x)) return false; return true; }
 inline bool is_finite(double x) { return std::isfinite(x); }

@@ -196,3 +196,43 @@ def test_kernel_source_equals_reference_run_fixtures(name):
         if name == "c4":
             exact = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c4_oracle_ext.json")))["grad_clean"]
         rf.check_gradient(hs.gradients(eps=1e-6)["grad"], ref, exact=exact)
+
+
+def operator_surface_model(**settings):
+    """Every statement form psy_lang.cuh documents: matrix*vector, matrix containers as vectors, %, element-wise /, unary minus,
+    scalar scaling and shifting, arma::exp / dot / accu / trans, x(i) and x[i], t (interval-local in the drift, absolute in the
+    measurement equation) and person."""
+    rng = np.random.default_rng(8)
+    N, T = 5, 9
+    obs = 0.5 + rng.standard_normal((N * T, 2))
+    obs[rng.random(obs.shape) < 0.1] = np.nan
+    kw = dict(
+        dataset={"person": np.repeat(np.arange(3, 3 + N), T), "observations": obs, "dt": np.tile(np.r_[0.0, np.full(T - 1, 0.6)], N)},
+        latentEquations=("dx = DRIFT*x + CINT;\n"
+                         "dx(0) = dx(0) + 0.01*arma::dot(x, x);\n"
+                         "dx = dx - 0.01*(x % x);\n"
+                         "dx = -(-dx);\n"
+                         "dx = dx + 0.001*arma::exp(-1.0*(x % x));\n"
+                         "dx[1] = dx[1] + 0.01*arma::accu(x) + 0.02*t;\n"
+                         "dx = dx/1.25;"),
+        manifestEquations=("y = arma::trans(LT)*x + MM;\n"
+                           "y = y + 0.01*(x/(x % x + 1.0));\n"
+                           "y(0) = y(0) + 0.1*sin(0.3*t) + 0.001*person;"),
+        parameters={"DRIFT": np.array([["d11 = -0.5", "0.1"], ["d21 = 0.2", "d22 = -0.6"]], dtype=object),
+                    "CINT": np.array([["c1 = 0.3"], ["0.1"]], dtype=object),
+                    "LT": np.array([["1", "l12 = 0.4"], ["0", "1"]], dtype=object),
+                    "MM": np.array([["0.2"], ["mm2 = -0.1"]], dtype=object)},
+        L=np.array([["l1 = 0.5", "0"], ["0.1", "l2 = 0.4"]], dtype=object),
+        Rchol=np.array([["r1 = 0.6", "0"], ["0.1", "r2 = 0.5"]], dtype=object),
+        A0=np.array([["0.8", "0"], ["0.1", "0.7"]], dtype=object), m0=np.array([["m1 = 1.0"], ["0.5"]], dtype=object),
+        integrateFunction="rk4", eps=np.array([1e-6]))
+    kw.update(settings)
+    return kw
+
+
+@pytest.mark.parametrize("settings", [{}, {"integrateFunction": "runge_kutta_dopri5"}, {"srUpdate": False}], ids=["rk4", "dopri5", "cov"])
+def test_operator_surface_of_the_equation_language(settings):
+    model = pd.newPsydiff(**operator_surface_model(**settings))
+    hs, _, _ = _check_fit(model)
+    if not settings:
+        _check_grad(model, hs, extended=True)

@@ -333,3 +333,11 @@ def test_random_model_structures(seed):
     from test_kernel_fuzz import random_model
     kw, _ = random_model(9000 + seed, stepper=("rk4", "runge_kutta_dopri5")[seed % 2], srUpdate=(seed % 3 != 2))
     _fit_pair(pd.newPsydiff(**dict(kw, breakEarly=False)))
+
+
+@pytest.mark.parametrize("settings", [{}, {"integrateFunction": "runge_kutta_dopri5"}, {"srUpdate": False}], ids=["rk4", "dopri5", "cov"])
+def test_operator_surface_of_the_equation_language(settings):
+    """The statement forms the kernel's equation language supports (tests/test_kernel_hostsim.py::operator_surface_model), as
+    Armadillo statements through the reference's own code."""
+    from test_kernel_hostsim import operator_surface_model
+    _fit_pair(pd.newPsydiff(**operator_surface_model(**settings)))
