@@ -484,3 +484,26 @@ def test_cpp_code_generator_errors():
     assert L.psy_emit_model_source(*args(nc=1), None, 0, C.byref(need)) == 1 and b"must include A0LogChol" in L.psy_last_error()
     with pytest.raises(ValueError, match="lower triangular"):          # the Python front end turns the C error into ValueError
         pd.newPsydiff(**synth.config_c1(N=3, T=4, A0=np.array([[1.0, 0.3], [0.0, 1.0]])))
+
+
+def test_product_code_never_touches_the_checkers():
+    """The package (Python and native sources) must not import, include or load anything under oracle/ or tests/: the oracle,
+    the reference build, the host-compiled kernel and the R stand-in are checkers, not fallbacks."""
+    pkg = os.path.join(ROOT, "psydiff_b200")
+    bad = []
+    for base, _, files in os.walk(pkg):
+        if "_kernel_cache" in base or "__pycache__" in base:
+            continue
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                continue
+            text = open(os.path.join(base, f)).read()
+            code = "\n".join(l.split("#")[0].split("//")[0] for l in text.splitlines())       # comments may name them
+            for pat in (r"\bimport\s+oracle\b", r"\bfrom\s+oracle\b", r"\bhostsim\b", r"reference_build", r"#include\s*[\"<].*oracle",
+                        r"#include\s*[\"<].*tests/", r"libpsy_oracle", r"r_stub"):
+                if re.search(pat, code):
+                    bad.append((f, pat))
+    assert bad == [], bad
+    # the one hook the kernel header has for the host compile is inert on the device
+    hdr = open(os.path.join(pkg, "csrc", "psy_filter.cuh")).read()
+    assert "#ifdef __CUDA_ARCH__" in hdr and hdr.count("psy_sim_rcp_seed") == 1
