@@ -341,3 +341,28 @@ def test_operator_surface_of_the_equation_language(settings):
     Armadillo statements through the reference's own code."""
     from test_kernel_hostsim import operator_surface_model
     _fit_pair(pd.newPsydiff(**operator_surface_model(**settings)))
+
+
+def test_package_defaults_integrate_function_default_and_time_step_ladder():
+    """newPsydiff's own defaults (R/prepareModel.R:399-406, 435-438): integrateFunction = "default" (rk4, dopri5 only if the
+    state came out non-finite) and timeStep = seq(min(dt)/30, min(dt)/10, length.out = 5), of which a finite first attempt uses
+    only the first entry; eps = c(1e-8, 1e-6, 1e-5, 1e-4)."""
+    kw = synth.config_c1(N=6, T=12)
+    for k in ("integrateFunction", "timeStep", "eps"):
+        kw.pop(k, None)
+    model = pd.newPsydiff(**kw)
+    assert model["integrateFunction"] == "default" and len(model["timeStep"]) == 5 and list(model["eps"]) == [1e-8, 1e-6, 1e-5, 1e-4]
+    assert model["timeStep"][0] == pytest.approx(1 / 30) and model["timeStep"][-1] == pytest.approx(1 / 10)
+    _fit_pair(model)
+    # the nonlinear model with its own irregular dt ladder
+    kw4 = synth.config_c4(N=3, T=6)
+    kw4.pop("integrateFunction", None)
+    m4 = pd.newPsydiff(**kw4)
+    assert m4["integrateFunction"] == "default"
+    _fit_pair(m4)
+    # eps[0] = 1e-8 resolves every side: the gradient uses only that step (noisier than 1e-6, same bookkeeping)
+    g = rb.Reference(model).gradients()
+    og = _oracle(model).gradients()
+    gv = np.array(list(g.values()))
+    atol = 64 * np.finfo(float).eps * abs(float(og["m2LL"].sum())) / 2e-8
+    assert np.all(np.abs(gv - og["grad_ref"]) <= 1e-6 * np.abs(og["grad_ref"]) + atol)
