@@ -70,6 +70,26 @@ __device__ __forceinline__ double rcp(double x) {
 #endif
 }
 
+// PREPARED EXPERIMENT (-DPSY_RSQRT_ROT, off by default; checked on the host through tests/hostsim, not yet timed on the device):
+// 1/sqrt(x) from the hardware seed (rsqrt.approx.ftz.f64) + two Newton steps, branch-free like rcp().  The Givens rotations of
+// the measurement update and the cholupdate steps then need no IEEE sqrt (≈ 16 instructions with a slow-path branch each) and
+// no reciprocal of the root: r = r²·r⁻¹, c = a·r⁻¹, s = b·r⁻¹.  sqrt(negative) = NaN either way; a ZERO radicand gives NaN here
+// and 0 (then inf) with sqrt — both non-finite outcomes of a failed downdate.
+__device__ __forceinline__ double rsq(double x) {
+  double y;
+#ifdef __CUDA_ARCH__
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+  y = psy_sim_rsqrt_seed(x);
+#endif
+  const double h = 0.5 * x;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  return y;
+}
+
 template <class Mdl>
 struct Filter {
   static constexpr int N = Mdl::N, M = Mdl::M, F = Mdl::NFREE;  // NFREE >= 1 (padded); NSLOT real slots
@@ -661,6 +681,13 @@ struct Filter {
       for (int k = 0; k < M; k++) {
         if (k < first) continue;
         const double a = S[tri(k, k)], b = tr[k];
+#ifdef PSY_RSQRT_ROT
+        const double r2 = a * a + b * b;
+        const double ri = rsq(r2);
+        const bool nz = r2 != 0.0;
+        const double r = nz ? r2 * ri : 0.0;
+        const double c = nz ? a * ri : 1.0, s = nz ? b * ri : 0.0;
+#else
         const double r = sqrt(a * a + b * b);
         double c = 1.0, s = 0.0;
         if (r != 0.0) {
@@ -668,6 +695,7 @@ struct Filter {
           c = a * ri;
           s = b * ri;
         }
+#endif
         S[tri(k, k)] = r;
 #pragma unroll
         for (int j = k + 1; j < M; j++) {
@@ -722,10 +750,19 @@ struct Filter {
 #pragma unroll
       for (int k = 0; k < M; k++) {
         const double lkk = S[tri(k, k)];
+#ifdef PSY_RSQRT_ROT
+        const double r2 = lkk * lkk + dir * x[k] * x[k];
+        const double ri = rsq(r2);
+        const double r = r2 * ri;
+        const double il = rcp(lkk);
+        const double c = r * il, s = x[k] * il;
+        const double ic = lkk * ri;
+#else
         const double r = sqrt(lkk * lkk + dir * x[k] * x[k]);
         const double il = rcp(lkk);
         const double c = r * il, s = x[k] * il;
         const double ic = lkk * rcp(r);
+#endif
         S[tri(k, k)] = r;
 #pragma unroll
         for (int i = k + 1; i < M; i++) {
@@ -754,10 +791,19 @@ struct Filter {
 #pragma unroll
       for (int k = 0; k < N; k++) {
         const double lkk = A[tri(k, k)];
+#ifdef PSY_RSQRT_ROT
+        const double r2 = lkk * lkk - x[k] * x[k];
+        const double ri = rsq(r2);
+        const double r = r2 * ri;
+        const double il = rcp(lkk);
+        const double c = r * il, s = x[k] * il;
+        const double ic = lkk * ri;
+#else
         const double r = sqrt(lkk * lkk - x[k] * x[k]);
         const double il = rcp(lkk);
         const double c = r * il, s = x[k] * il;
         const double ic = lkk * rcp(r);
+#endif
         A[tri(k, k)] = r;
 #pragma unroll
         for (int i = k + 1; i < N; i++) {

@@ -33,4 +33,13 @@ static inline double psy_sim_rcp_seed(double x) {
   return r;
 }
 
+// rsqrt.approx.ftz.f64: same convention (low 32 bits zero)
+static inline double psy_sim_rsqrt_seed(double x) {
+  double r = 1.0 / sqrt(x);
+  uint64_t b; memcpy(&b, &r, sizeof b);
+  b &= 0xffffffff00000000ULL;
+  memcpy(&r, &b, sizeof r);
+  return r;
+}
+
 namespace psy { double psy_smem[1 << 14]; }  // dynamic shared memory of the ONE simulated thread block (single host thread)

@@ -173,7 +173,7 @@ def test_instance_list_padding_and_parameter_sets_do_not_change_results():
         assert np.array_equal(many[k], hs.fit(theta=sets[k], states=False)["m2LL"])
 
 
-@pytest.mark.parametrize("flags", ["-DPSY_RHS_SCALED=0", "-DPSY_RK4_SMEM=1", "-DPSY_RK4_SMEM=0", "-DPSY_IEEE_DIV"])
+@pytest.mark.parametrize("flags", ["-DPSY_RHS_SCALED=0", "-DPSY_RK4_SMEM=1", "-DPSY_RK4_SMEM=0", "-DPSY_IEEE_DIV", "-DPSY_RSQRT_ROT"])
 def test_compile_time_variants_agree(flags):
     """Every compile-time variant of the kernel computes the same filter (to rounding)."""
     for kw in (synth.config_c4(N=4, T=8), synth.config_coupled(K=4, N=3, T=6)):
