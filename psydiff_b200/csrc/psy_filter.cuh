@@ -683,10 +683,10 @@ struct Filter {
         const double a = S[tri(k, k)], b = tr[k];
 #ifdef PSY_RSQRT_ROT
         const double r2 = a * a + b * b;
-        const double ri = rsq(r2);
         const bool nz = r2 != 0.0;
-        const double r = nz ? r2 * ri : 0.0;
-        const double c = nz ? a * ri : 1.0, s = nz ? b * ri : 0.0;
+        const double ri = nz ? rsq(r2) : 0.0;      // a = b = 0: identity rotation (r = 0, c = 1, s = 0)
+        const double r = r2 * ri, s = b * ri;
+        const double c = nz ? a * ri : 1.0;
 #else
         const double r = sqrt(a * a + b * b);
         double c = 1.0, s = 0.0;
