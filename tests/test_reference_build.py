@@ -366,3 +366,22 @@ def test_package_defaults_integrate_function_default_and_time_step_ladder():
     gv = np.array(list(g.values()))
     atol = 64 * np.finfo(float).eps * abs(float(og["m2LL"].sum())) / 2e-8
     assert np.all(np.abs(gv - og["grad_ref"]) <= 1e-6 * np.abs(og["grad_ref"]) + atol)
+
+
+@pytest.mark.parametrize("direction", ["left", "right"])
+def test_one_sided_gradients(direction):
+    """direction = "left" / "right" (R/modelTemplate.R:872-879, 900-902, 920-922): the other side is the unperturbed Σ-2LL and the
+    denominator is the one step used."""
+    model = pd.newPsydiff(**synth.config_c1(N=6, T=10, direction=direction))
+    g = np.array(list(rb.Reference(model).gradients().values()))
+    og = _oracle(model).gradients(direction=direction)
+    atol = 64 * np.finfo(float).eps * abs(float(og["m2LL"].sum())) / 1e-6
+    assert np.all(np.abs(g - og["grad_ref"]) <= 1e-6 * np.abs(og["grad_ref"]) + atol)
+    central = _oracle(pd.newPsydiff(**synth.config_c1(N=6, T=10))).gradients()["grad_clean"]
+    assert np.allclose(g, central, rtol=1e-3, atol=1e-3 * np.abs(central).max())        # first-order accurate: close to the central one
+
+
+def test_unknown_direction_is_an_error():
+    model = pd.newPsydiff(**synth.config_c1(N=3, T=5, direction="sideways"))
+    with pytest.raises(RuntimeError, match="Unknown direction argument. Possible are central, left and right"):
+        rb.Reference(model).gradients()
