@@ -562,7 +562,11 @@ int psy_oracle_fit(const psy_oracle_problem* q, const double* theta, double* m2l
 // getGradients (R/modelTemplate.R:852-930).  direction: 0 central, 1 left, 2 right.  Perturbs from a pristine copy of
 // theta (quirk Q7).  Only persons whose theta_index touches `par` are re-filtered (dirty-flag semantics,
 // psydiffBasic.h:22-26 / R/modelTemplate.R:248-254); all others keep their base -2LL.
-// grad_ref : literal reference arithmetic (Σ right − Σ left)/Σ eps in double, sequential sums over persons.
+// Every evaluation is independent of the ones before it: the reference's history effects — the shared parameter list (quirk
+// Q4) and the NaN poisoning of a model object after one non-finite evaluation (quirk Q8: results are "reset" by x -= x,
+// R/modelTemplate.R:255-261, so its eps[] fallback never recovers) — are deliberately not reproduced; both are pinned by
+// tests/test_reference_build.py against the reference's own code.
+// grad_ref : the reference's arithmetic (Σ right − Σ left)/Σ eps in double, sequential sums over persons.
 // grad_clean: Σ_p (f+_p − f−_p) accumulated in long double — the parity target for the GPU path.
 int psy_oracle_gradients(const psy_oracle_problem* q, const double* theta, const double* eps, int n_eps, int direction,
                          double* grad_ref, double* grad_clean, double* base_m2ll_out, int nthreads) {
