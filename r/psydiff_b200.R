@@ -34,41 +34,48 @@ psydiffCudaSource <- function(nlatent, nmanifest, latentEquations, manifestEquat
 .psy_settings <- function(m) list(c(m$alpha, m$beta, m$kappa), .psy_stepper(m$integrateFunction), as.numeric(m$timeStep),
                                   isTRUE(m$srUpdate) || is.null(m$srUpdate))
 
+# Make the handle hold THIS model's dataset and slot map (re-upload only when it is handed different R objects).
+.psy_sync <- function(handle, m) {
+  pt <- m$pars$parameterTable
+  if (!.Call("R_psy_is_current", handle, m$data$observations, m$data$dt, m$data$person, pt$label)) {
+    persons <- unique(m$data$person)
+    labs <- unique(pt$label)                                   # theta, first-appearance order
+    tidx <- as.integer(match(pt$label, labs) - 1L)             # person-major, slot-minor: exactly psy_set_slots' layout
+    off <- c(0, cumsum(rle(as.vector(m$data$person))$lengths))
+    .Call("R_psy_upload", handle, m$data$observations, m$data$dt, m$data$person, as.numeric(off), as.integer(persons),
+          length(labs), tidx, pt$label)
+  }
+  invisible(NULL)
+}
+
+# compileModel(psydiffModel) is called for its side effect, like the reference's (R/prepareModel.R:553-562): it defines
+# fitModel / getGradients / getGradient in the global environment.  The compiled kernel and the resident dataset live in
+# `handle`, captured by those closures (the counterpart of the shared object Rcpp::sourceCpp loads); the functions accept
+# any model object of the same structure, as the reference's do.
 compileModel <- function(psydiffModel) {
-  pt <- psydiffModel$pars$parameterTable
-  persons <- unique(psydiffModel$data$person)
-  labs <- unique(pt$label)                                   # theta, first-appearance order
-  nfree <- nrow(pt) / length(persons)
-  tidx <- as.integer(match(pt$label, labs) - 1L)             # person-major, slot-minor: exactly psy_set_slots' layout
-  off <- c(0, cumsum(rle(as.vector(psydiffModel$data$person))$lengths))
-  psydiffModel$handle <- .Call("R_psy_compile", psydiffModel$cppCode, system.file("include", package = "psydiff"),
-                               tools::R_user_dir("psydiff", "cache"), psydiffModel$nlatent, psydiffModel$nmanifest, nfree,
-                               psydiffModel$data$observations, as.numeric(psydiffModel$data$dt), as.numeric(off),
-                               as.integer(persons), length(labs), tidx)
+  nfree <- nrow(psydiffModel$pars$parameterTable) / length(unique(psydiffModel$data$person))
+  handle <- .Call("R_psy_compile", psydiffModel$cppCode, system.file("include", package = "psydiff"),
+                  tools::R_user_dir("psydiff", "cache"), psydiffModel$nlatent, psydiffModel$nmanifest, nfree)
   assign("fitModel", function(psydiffModel, skipUpdate = FALSE) {
+    .psy_sync(handle, psydiffModel)
     s <- .psy_settings(psydiffModel)
-    out <- .Call("R_psy_fit", psydiffModel$handle, s[[1]], s[[2]], s[[3]], s[[4]], getParameterValues(psydiffModel), skipUpdate,
-                 length(unique(psydiffModel$data$person)), nrow(psydiffModel$data$observations), psydiffModel$nlatent,
-                 psydiffModel$nmanifest)
-    psydiffModel$pars$parameterTable$changed <- FALSE       # the reference clears the flags by reference (R/modelTemplate.R:410)
-    out
+    # overwrites psydiffModel$m2LL / $latentScores / $predictedManifest and clears parameterTable$changed IN PLACE, as the
+    # reference does through Rcpp (R/modelTemplate.R:410-414), and returns list(latentScores, predictedManifest, m2LL)
+    .Call("R_psy_fit", handle, psydiffModel, s[[1]], s[[2]], s[[3]], s[[4]], getParameterValues(psydiffModel), skipUpdate)
   }, envir = globalenv())
   assign("getGradients", function(psydiffModel) {
+    .psy_sync(handle, psydiffModel)
     s <- .psy_settings(psydiffModel)
-    theta <- getParameterValues(psydiffModel)
-    g <- .Call("R_psy_gradients", psydiffModel$handle, s[[1]], s[[2]], s[[3]], s[[4]], theta, as.numeric(psydiffModel$eps),
-               .psy_direction(psydiffModel$direction))
-    names(g) <- names(theta)
-    g
+    .Call("R_psy_gradients", handle, s[[1]], s[[2]], s[[3]], s[[4]], getParameterValues(psydiffModel),
+          as.numeric(psydiffModel$eps), .psy_direction(psydiffModel$direction))
   }, envir = globalenv())
   assign("getGradient", function(psydiffModel, currentParameterValues, par) {
+    .psy_sync(handle, psydiffModel)
     s <- .psy_settings(psydiffModel)
-    g <- .Call("R_psy_gradient", psydiffModel$handle, s[[1]], s[[2]], s[[3]], s[[4]], currentParameterValues, as.integer(par),
-               as.numeric(psydiffModel$eps), .psy_direction(psydiffModel$direction))
-    names(g) <- names(currentParameterValues)[par + 1]
-    g
+    .Call("R_psy_gradient", handle, s[[1]], s[[2]], s[[3]], s[[4]], currentParameterValues, as.integer(par),
+          as.numeric(psydiffModel$eps), .psy_direction(psydiffModel$direction))
   }, envir = globalenv())
-  invisible(psydiffModel)
+  invisible(NULL)
 }
 
 # the PSOCK cluster of the reference is not needed: the whole parameter sweep is one batched launch

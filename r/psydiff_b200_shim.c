@@ -64,24 +64,51 @@ SEXP R_psy_emit_source(SEXP n, SEXP m, SEXP n_slots, SEXP latent, SEXP manifest,
   return Rf_mkString(buf);
 }
 
-/* ---- compileModel(psydiffModel) — R/prepareModel.R:553-562 ---------------------------------------------------------- */
-SEXP R_psy_compile(SEXP cuda_src, SEXP incdir, SEXP cachedir, SEXP n, SEXP m, SEXP nfree, SEXP obs, SEXP dt,
-                   SEXP person_off, SEXP person_id, SEXP n_theta, SEXP theta_index) {
+/* ---- compileModel(psydiffModel) — R/prepareModel.R:553-562 ----------------------------------------------------------
+ * The reference's compileModel only loads compiled code; the functions it defines work on ANY model object of the same
+ * structure, reading model$data on every call.  Here the dataset is resident in HBM, so the handle remembers WHICH R
+ * objects it holds (observations, dt, person, parameterTable$label — kept alive in the external pointer's protected slot)
+ * and R_psy_is_current lets the R wrappers re-upload when they are handed different ones.  R's copy-on-modify makes object
+ * identity a sound test: a modified dataset is a new object. */
+SEXP R_psy_compile(SEXP cuda_src, SEXP incdir, SEXP cachedir, SEXP n, SEXP m, SEXP nfree) {
   char cubin[4096];
   CHECK(psy_model_compile(CHAR(STRING_ELT(cuda_src, 0)), CHAR(STRING_ELT(incdir, 0)), CHAR(STRING_ELT(cachedir, 0)), "",
                           cubin, sizeof cubin));
   psy_model* mdl = psy_model_create(Rf_asInteger(n), Rf_asInteger(m), Rf_asInteger(nfree), cubin);
   if (!mdl) Rf_error("%s", psy_last_error());
+  SEXP held = PROTECT(Rf_allocVector(VECSXP, 4));
+  SEXP p = PROTECT(R_MakeExternalPtr(mdl, R_NilValue, held));
+  R_RegisterCFinalizerEx(p, model_finalizer, TRUE);
+  UNPROTECT(2);
+  return p;
+}
+
+SEXP R_psy_is_current(SEXP h, SEXP obs, SEXP dt, SEXP person, SEXP labels) {
+  model_of(h);
+  SEXP held = R_ExternalPtrProtected(h);
+  const int same = VECTOR_ELT(held, 0) == obs && VECTOR_ELT(held, 1) == dt && VECTOR_ELT(held, 2) == person &&
+                   VECTOR_ELT(held, 3) == labels;
+  SEXP out = PROTECT(Rf_allocVector(LGLSXP, 1));
+  LOGICAL(out)[0] = same;
+  UNPROTECT(1);
+  return out;
+}
+
+/* model$data -> HBM and the slot map (theta_index = match(label, unique(label)) - 1, person-major) */
+SEXP R_psy_upload(SEXP h, SEXP obs, SEXP dt, SEXP person, SEXP person_off, SEXP person_id, SEXP n_theta, SEXP theta_index,
+                  SEXP labels) {
+  psy_model* mdl = model_of(h);
   const int N = LENGTH(person_id);
   int64_t* off = (int64_t*)R_alloc((size_t)N + 1, sizeof(int64_t));
   for (int i = 0; i <= N; i++) off[i] = (int64_t)REAL(person_off)[i];
-  int rc = psy_upload(mdl, (int64_t)LENGTH(dt), N, REAL(obs), REAL(dt), off, INTEGER(person_id));
-  if (rc == PSY_OK) rc = psy_set_slots(mdl, Rf_asInteger(n_theta), INTEGER(theta_index));
-  if (rc != PSY_OK) { psy_model_destroy(mdl); Rf_error("%s", psy_last_error()); }
-  SEXP p = PROTECT(R_MakeExternalPtr(mdl, R_NilValue, R_NilValue));
-  R_RegisterCFinalizerEx(p, model_finalizer, TRUE);
-  UNPROTECT(1);
-  return p;
+  CHECK(psy_upload(mdl, (int64_t)LENGTH(dt), N, REAL(obs), REAL(dt), off, INTEGER(person_id)));
+  CHECK(psy_set_slots(mdl, Rf_asInteger(n_theta), INTEGER(theta_index)));
+  SEXP held = R_ExternalPtrProtected(h);
+  SET_VECTOR_ELT(held, 0, obs);
+  SET_VECTOR_ELT(held, 1, dt);
+  SET_VECTOR_ELT(held, 2, person);
+  SET_VECTOR_ELT(held, 3, labels);
+  return R_NilValue;
 }
 
 /* a changed model$integrateFunction / srUpdate needs the matching kernel (R/modelTemplate.R:174) */
@@ -98,15 +125,34 @@ static void push_settings(psy_model* mdl, SEXP settings, SEXP stepper, SEXP time
                            REAL(timeStep), LENGTH(timeStep), Rf_asLogical(sr)));
 }
 
-/* fitModel(psydiffModel, skipUpdate) — R/modelTemplate.R:165-420; returns list(latentScores, predictedManifest, m2LL) */
-SEXP R_psy_fit(SEXP h, SEXP settings, SEXP stepper, SEXP timeStep, SEXP sr, SEXP theta, SEXP skip, SEXP N, SEXP rows,
-               SEXP n, SEXP m) {
+/* list[name] = value on the list object itself (what Rcpp's `psydiffModel["m2LL"] = m2LL` does); a missing element is an error */
+static void list_set(SEXP list, const char* name, SEXP value) {
+  SEXP names = Rf_getAttrib(list, R_NamesSymbol);
+  if (names != R_NilValue)
+    for (int i = 0; i < LENGTH(names); i++)
+      if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) { SET_VECTOR_ELT(list, i, value); return; }
+  Rf_error("element '%s' not found", name);
+}
+
+/* fitModel(psydiffModel, skipUpdate) — R/modelTemplate.R:165-420.  Returns list(latentScores, predictedManifest, m2LL) AND, like
+ * the reference (which works on the Rcpp::List by reference, R/modelTemplate.R:410-414; relied on at R/prepareModel.R:286),
+ * overwrites model$m2LL / $latentScores / $predictedManifest in place and clears pars$parameterTable$changed. */
+SEXP R_psy_fit(SEXP h, SEXP model, SEXP settings, SEXP stepper, SEXP timeStep, SEXP sr, SEXP theta, SEXP skip) {
   psy_model* mdl = model_of(h);
   push_settings(mdl, settings, stepper, timeStep, sr);
-  SEXP m2 = PROTECT(Rf_allocVector(REALSXP, Rf_asInteger(N)));
-  SEXP ls = PROTECT(real_matrix(Rf_asInteger(rows), Rf_asInteger(n)));
-  SEXP pm = PROTECT(real_matrix(Rf_asInteger(rows), Rf_asInteger(m)));
+  SEXP obs = list_get(list_get(model, "data"), "observations");
+  const int rows = Rf_nrows(obs), m = Rf_ncols(obs), n = Rf_asInteger(list_get(model, "nlatent"));
+  const int N = LENGTH(list_get(model, "m2LL"));
+  SEXP m2 = PROTECT(Rf_allocVector(REALSXP, N));
+  SEXP ls = PROTECT(real_matrix(rows, n));
+  SEXP pm = PROTECT(real_matrix(rows, m));
   CHECK(psy_fit(mdl, REAL(theta), Rf_asLogical(skip), REAL(m2), REAL(ls), REAL(pm)));
+  /* by-reference side effects on the caller's model object: psydiffModel["m2LL"] = m2LL; ... (R/modelTemplate.R:412-414) */
+  list_set(model, "m2LL", m2);
+  list_set(model, "latentScores", ls);
+  list_set(model, "predictedManifest", pm);
+  SEXP changed = list_get(list_get(list_get(model, "pars"), "parameterTable"), "changed");
+  for (int i = 0; i < LENGTH(changed); i++) LOGICAL(changed)[i] = 0;      /* :410 */
   SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
   SET_VECTOR_ELT(out, 0, ls);
   SET_VECTOR_ELT(out, 1, pm);
@@ -120,13 +166,15 @@ SEXP R_psy_fit(SEXP h, SEXP settings, SEXP stepper, SEXP timeStep, SEXP sr, SEXP
   return out;
 }
 
-/* getGradients(psydiffModel) — R/modelTemplate.R:852-930; direction: 0 central, 1 left, 2 right */
+/* getGradients(psydiffModel) — R/modelTemplate.R:852-930; direction: 0 central, 1 left, 2 right.  Named like
+ * getParameterValues; the model object is not modified (the reference works on a clone, :855). */
 SEXP R_psy_gradients(SEXP h, SEXP settings, SEXP stepper, SEXP timeStep, SEXP sr, SEXP theta, SEXP eps, SEXP direction) {
   psy_model* mdl = model_of(h);
   push_settings(mdl, settings, stepper, timeStep, sr);
   SEXP g = PROTECT(Rf_allocVector(REALSXP, LENGTH(theta)));
   double total;
   CHECK(psy_gradients(mdl, REAL(theta), REAL(eps), LENGTH(eps), Rf_asInteger(direction), REAL(g), &total));
+  Rf_setAttrib(g, R_NamesSymbol, Rf_getAttrib(theta, R_NamesSymbol));
   UNPROTECT(1);
   return g;
 }
@@ -137,7 +185,16 @@ SEXP R_psy_gradient(SEXP h, SEXP settings, SEXP stepper, SEXP timeStep, SEXP sr,
   push_settings(mdl, settings, stepper, timeStep, sr);
   double g;
   CHECK(psy_gradient(mdl, REAL(theta), Rf_asInteger(par), REAL(eps), LENGTH(eps), Rf_asInteger(direction), &g));
-  return Rf_ScalarReal(g);
+  SEXP out = PROTECT(Rf_ScalarReal(g));
+  SEXP names = Rf_getAttrib(theta, R_NamesSymbol);
+  if (names != R_NilValue && Rf_asInteger(par) >= 0 && Rf_asInteger(par) < LENGTH(names)) {
+    SEXP nm = PROTECT(Rf_allocVector(STRSXP, 1));
+    SET_STRING_ELT(nm, 0, STRING_ELT(names, Rf_asInteger(par)));
+    Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(1);
+  }
+  UNPROTECT(1);
+  return out;
 }
 
 /* ---- parameter plumbing with the reference's by-reference semantics (inst/include/psydiffBasic.h) --------------------- */
@@ -369,9 +426,11 @@ static const R_CallMethodDef CallEntries[] = {
     {"_psydiff_logChol2Chol", (DL_FUNC)&_psydiff_logChol2Chol, 1},
     {"_psydiff_clonePsydiffModel", (DL_FUNC)&_psydiff_clonePsydiffModel, 1},
     {"R_psy_emit_source", (DL_FUNC)&R_psy_emit_source, 11},
-    {"R_psy_compile", (DL_FUNC)&R_psy_compile, 12},
+    {"R_psy_compile", (DL_FUNC)&R_psy_compile, 6},
+    {"R_psy_is_current", (DL_FUNC)&R_psy_is_current, 5},
+    {"R_psy_upload", (DL_FUNC)&R_psy_upload, 9},
     {"R_psy_load_module", (DL_FUNC)&R_psy_load_module, 4},
-    {"R_psy_fit", (DL_FUNC)&R_psy_fit, 11},
+    {"R_psy_fit", (DL_FUNC)&R_psy_fit, 8},
     {"R_psy_gradients", (DL_FUNC)&R_psy_gradients, 8},
     {"R_psy_gradient", (DL_FUNC)&R_psy_gradient, 9},
     {NULL, NULL, 0}};

@@ -67,6 +67,8 @@ SEXP R_MakeExternalPtr(void* p, SEXP tag, SEXP prot);
 void* R_ExternalPtrAddr(SEXP s);
 void R_ClearExternalPtr(SEXP s);
 void R_RegisterCFinalizerEx(SEXP s, R_CFinalizer_t fun, Rboolean onexit);
+SEXP R_ExternalPtrProtected(SEXP s);
+void R_SetExternalPtrProtected(SEXP s, SEXP p);
 
 #ifdef __cplusplus
 }

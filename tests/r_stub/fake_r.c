@@ -12,12 +12,12 @@
 struct psy_rstub_sexp {
   int type, len;
   void* data;           /* double[] / int[] / SEXP[] / char[] / external pointer */
-  SEXP names, dim;
+  SEXP names, dim, prot;
   R_CFinalizer_t fin;
 };
 
-static struct psy_rstub_sexp nil_obj = {NILSXP, 0, NULL, NULL, NULL, NULL}, names_sym = {NILSXP, 0, NULL, NULL, NULL, NULL},
-                             dim_sym = {NILSXP, 0, NULL, NULL, NULL, NULL};
+static struct psy_rstub_sexp nil_obj = {NILSXP, 0, NULL, NULL, NULL, NULL, NULL}, names_sym = {NILSXP, 0, NULL, NULL, NULL, NULL, NULL},
+                             dim_sym = {NILSXP, 0, NULL, NULL, NULL, NULL, NULL};
 SEXP R_NilValue = &nil_obj, R_NamesSymbol = &names_sym, R_DimSymbol = &dim_sym;
 
 static jmp_buf* cur_jmp = NULL;
@@ -28,7 +28,7 @@ static SEXP new_sexp(int type, int len, size_t elem) {
   SEXP s = (SEXP)calloc(1, sizeof *s);
   s->type = type; s->len = len;
   s->data = calloc((size_t)(len > 0 ? len : 1), elem);
-  s->names = s->dim = R_NilValue;
+  s->names = s->dim = s->prot = R_NilValue;
   return s;
 }
 
@@ -97,7 +97,9 @@ void Rf_error(const char* fmt, ...) {
 void Rf_warning(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(warn_msg, sizeof warn_msg, fmt, ap); va_end(ap); n_warnings++; }
 char* R_alloc(size_t n, int size) { return (char*)calloc(n > 0 ? n : 1, (size_t)size); }
 
-SEXP R_MakeExternalPtr(void* p, SEXP tag, SEXP prot) { (void)tag; (void)prot; SEXP s = new_sexp(EXTPTRSXP, 0, 1); free(s->data); s->data = p; return s; }
+SEXP R_MakeExternalPtr(void* p, SEXP tag, SEXP prot) { (void)tag; SEXP s = new_sexp(EXTPTRSXP, 0, 1); free(s->data); s->data = p; s->prot = prot; return s; }
+SEXP R_ExternalPtrProtected(SEXP s) { return s->prot; }
+void R_SetExternalPtrProtected(SEXP s, SEXP p) { s->prot = p; }
 void* R_ExternalPtrAddr(SEXP s) { return s->type == EXTPTRSXP ? s->data : NULL; }
 void R_ClearExternalPtr(SEXP s) { s->data = NULL; }
 void R_RegisterCFinalizerEx(SEXP s, R_CFinalizer_t fun, Rboolean onexit) { (void)onexit; s->fin = fun; }

@@ -140,7 +140,8 @@ def test_registration_table_matches_the_reference(r):
     got = {r.L.psy_rstub_registered_name(k).decode(): r.L.psy_rstub_registered_arity(k) for k in range(r.L.psy_rstub_n_registered())}
     for name, arity in REFERENCE_TABLE.items():
         assert got.get(name) == arity, name
-    assert set(got) - set(REFERENCE_TABLE) == {"R_psy_emit_source", "R_psy_compile", "R_psy_load_module", "R_psy_fit", "R_psy_gradients", "R_psy_gradient"}
+    assert set(got) - set(REFERENCE_TABLE) == {"R_psy_emit_source", "R_psy_compile", "R_psy_is_current", "R_psy_upload", "R_psy_load_module",
+                                               "R_psy_fit", "R_psy_gradients", "R_psy_gradient"}
     assert r.L.psy_rstub_dynamic_symbols() == 0          # R_useDynamicSymbols(dll, FALSE), src/RcppExports.cpp:320
     with pytest.raises(RuntimeError, match="Incorrect number of arguments"):
         r.call("_psydiff_getPhi", r.num(np.eye(2)), r.num([1.0]))
@@ -296,14 +297,36 @@ def test_compute_entry_points_fail_loudly_without_a_device(r):
 
 
 def _compile(r, model):
-    """compileModel of r/psydiff_b200.R, argument by argument."""
-    pt = model["pars"]["parameterTable"]
+    """compileModel of r/psydiff_b200.R: compile + load only; the data follow through .psy_sync."""
     spec = model["_spec"]
-    obs = np.asfortranarray(model["data"]["observations"])
     return r.call("R_psy_compile", r.chr(model["cppCode"]), r.chr(_lib.CSRC_DIR), r.chr(_lib.CACHE_DIR), r.int([spec.nlatent]),
-                  r.int([spec.nmanifest]), r.int([spec.n_slots]), r.num(obs), r.num(model["data"]["dt"]),
-                  r.num(np.asarray(model["_row_off"], dtype=float)), r.int(np.asarray(model["_persons_unique"], dtype=np.int32)),
-                  r.int([len(pt.theta_labels)]), r.int(np.ascontiguousarray(pt.theta_index, dtype=np.int32).reshape(-1)))
+                  r.int([spec.nmanifest]), r.int([spec.n_slots]))
+
+
+def _r_model(r, model):
+    """The psydiffModel list as R holds it (the fields the wrappers and the shim read)."""
+    obs = np.asfortranarray(model["data"]["observations"])
+    N, rows = len(model["_persons_unique"]), obs.shape[0]
+    return r.list({"pars": r.list({"parameterTable": _parameter_table(r, model)}),
+                   "nlatent": r.int([model["nlatent"]]), "nmanifest": r.int([model["nmanifest"]]),
+                   "data": r.list({"person": r.num(np.asarray(model["data"]["person"], dtype=float)), "observations": r.num(obs),
+                                   "dt": r.num(model["data"]["dt"])}),
+                   "m2LL": r.num(np.zeros(N)), "predictedManifest": r.num(np.full((rows, model["nmanifest"]), -99999.99)),
+                   "latentScores": r.num(np.full((rows, model["nlatent"]), -99999.99))})
+
+
+def _sync(r, h, rm, model):
+    """.psy_sync of r/psydiff_b200.R; returns whether an upload happened."""
+    L = r.L
+    data, pt = L.VECTOR_ELT(rm, 3), L.VECTOR_ELT(L.VECTOR_ELT(rm, 0), 0)
+    person, obs, dt, labels = L.VECTOR_ELT(data, 0), L.VECTOR_ELT(data, 1), L.VECTOR_ELT(data, 2), L.VECTOR_ELT(pt, 0)
+    if r.py(r.call("R_psy_is_current", h, obs, dt, person, labels))[0]:
+        return False
+    ptab = model["pars"]["parameterTable"]
+    r.call("R_psy_upload", h, obs, dt, person, r.num(np.asarray(model["_row_off"], dtype=float)),
+           r.int(np.asarray(model["_persons_unique"], dtype=np.int32)), r.int([len(ptab.theta_labels)]),
+           r.int(np.ascontiguousarray(ptab.theta_index, dtype=np.int32).reshape(-1)), labels)
+    return True
 
 
 @pytest.mark.gpu
@@ -313,20 +336,33 @@ def test_compile_fit_and_gradients_through_the_shim_on_the_gpu(r):
     fit = pd.fitModel(model)
     g = pd.getGradients(model)
     h = _compile(r, model)
+    rm = _r_model(r, model)
     settings = (r.num([model["alpha"], model["beta"], model["kappa"]]), r.int([0]), r.num(model["timeStep"]), r.lgl(True))
-    theta = r.num(model["pars"]["parameterTable"].theta_values)
-    rows, N = model["data"]["observations"].shape[0], len(model["_persons_unique"])
-    out = r.py(r.call("R_psy_fit", h, *settings, theta, r.lgl(False), r.int([N]), r.int([rows]), r.int([6]), r.int([6])))
-    assert list(out) == ["latentScores", "predictedManifest", "m2LL"]         # R/modelTemplate.R:416-419
+    theta = r.call("_psydiff_getParameterValues", rm)
+    with pytest.raises(RuntimeError, match="psy_upload|psy_set_slots"):               # nothing resident yet
+        r.call("R_psy_fit", h, rm, *settings, theta, r.lgl(False))
+    assert _sync(r, h, rm, model) is True and _sync(r, h, rm, model) is False          # uploads once for the same R objects
+    out = r.py(r.call("R_psy_fit", h, rm, *settings, theta, r.lgl(False)))
+    assert list(out) == ["latentScores", "predictedManifest", "m2LL"]                   # R/modelTemplate.R:416-419
     assert np.array_equal(out["m2LL"], fit["m2LL"]) and np.array_equal(out["latentScores"], fit["latentScores"])
     assert np.array_equal(out["predictedManifest"], fit["predictedManifest"])
-    gr = r.py(r.call("R_psy_gradients", h, *settings, theta, r.num(model["eps"]), r.int([0])))
-    assert np.array_equal(gr, np.array(list(g.values())))
-    one = r.py(r.call("R_psy_gradient", h, *settings, theta, r.int([4]), r.num(model["eps"]), r.int([0])))
-    assert one[0] == gr[4]
+    after = r.py(rm)                                                                    # by-reference side effects on the model
+    assert np.array_equal(after["m2LL"], fit["m2LL"]) and np.array_equal(after["latentScores"], fit["latentScores"])
+    assert not after["pars"]["parameterTable"]["changed"].any()
+    gr = r.call("R_psy_gradients", h, *settings, theta, r.num(model["eps"]), r.int([0]))
+    assert r.names(gr) == list(g) and np.array_equal(r.py(gr), np.array(list(g.values())))
+    one = r.call("R_psy_gradient", h, *settings, theta, r.int([4]), r.num(model["eps"]), r.int([0]))
+    assert r.py(one)[0] == r.py(gr)[4] and r.names(one) == [list(g)[4]]
     with pytest.raises(RuntimeError, match="Unknown direction"):
         r.call("R_psy_gradients", h, *settings, theta, r.num(model["eps"]), r.int([7]))
-    r.L.psy_rstub_run_finalizer(h)                                            # what R's GC does with the external pointer
+    # a different dataset object of the same structure: the wrappers re-upload and the functions work on it (as the reference's do)
+    model2 = pd.newPsydiff(**synth.config_c4(N=4, T=6, seed=77))
+    pd.compileModel(model2)
+    rm2 = _r_model(r, model2)
+    assert _sync(r, h, rm2, model2) is True
+    out2 = r.py(r.call("R_psy_fit", h, rm2, *settings[:2], r.num(model2["timeStep"]), settings[3], r.call("_psydiff_getParameterValues", rm2), r.lgl(False)))
+    assert np.array_equal(out2["m2LL"], pd.fitModel(model2)["m2LL"])
+    r.L.psy_rstub_run_finalizer(h)                                                      # what R's GC does with the external pointer
     assert not r.L.R_ExternalPtrAddr(h)
     with pytest.raises(RuntimeError, match="model is not compiled"):
         r.call("R_psy_gradients", h, *settings, theta, r.num(model["eps"]), r.int([0]))
