@@ -29,17 +29,21 @@ REFERENCE_TABLE = {"_psydiff_setParameterValues": 3, "_psydiff_getParameterValue
 class R:
     """Just enough of an R session: builds stand-in SEXPs from Python values, .Call()s registered routines, reads results."""
 
-    def __init__(self):
+    def __init__(self, mock_device=False):
+        """mock_device=True links the shim against tests/r_stub/mock_device.c ahead of the real library: the device entry points
+        (compile, upload, fit, gradients) become trivial host stand-ins so the whole flow runs without a GPU."""
         _lib.lib()                                         # libpsydiff_b200.so built (conftest) before linking against it
         out = os.path.join(STUB, "_build")
         os.makedirs(out, exist_ok=True)
-        so = os.path.join(out, "libpsydiff_rshim.so")
+        so = os.path.join(out, "libpsydiff_rshim_mock.so" if mock_device else "libpsydiff_rshim.so")
         srcs = [os.path.join(ROOT, "r", "psydiff_b200_shim.c"), os.path.join(STUB, "fake_r.c")]
+        if mock_device:
+            srcs.append(os.path.join(STUB, "mock_device.c"))   # same link unit: its definitions of the device entry points win
         deps = srcs + [os.path.join(STUB, h) for h in ("Rinternals.h", "R.h", "R_ext/Rdynload.h")] + \
             [os.path.join(ROOT, "include", "psydiff_b200.h"), _lib.LIB_PATH]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             libdir = os.path.dirname(_lib.LIB_PATH)
-            cmd = ["gcc", "-std=c11", "-O1", "-g", "-shared", "-fPIC", "-Wall", "-Wextra", "-Werror", "-Wno-cast-function-type", "-I", STUB, "-I",
+            cmd = ["gcc", "-std=gnu11", "-O1", "-g", "-shared", "-fPIC", "-Wall", "-Wextra", "-Werror", "-Wno-cast-function-type", "-I", STUB, "-I",
                    os.path.join(ROOT, "include"), "-o", so] + srcs + ["-L", libdir, "-lpsydiff_b200", f"-Wl,-rpath,{libdir}"]
             r = subprocess.run(cmd, capture_output=True, text=True)
             assert r.returncode == 0, r.stderr
@@ -327,6 +331,54 @@ def _sync(r, h, rm, model):
            r.int(np.asarray(model["_persons_unique"], dtype=np.int32)), r.int([len(ptab.theta_labels)]),
            r.int(np.ascontiguousarray(ptab.theta_index, dtype=np.int32).reshape(-1)), labels)
     return True
+
+
+def test_compile_sync_fit_gradient_flow_with_a_mock_device():
+    """The whole R-side flow of r/psydiff_b200.R through the shim, the device entry points replaced by tests/r_stub/mock_device.c:
+    compile -> sync (upload once per dataset object) -> fit with the reference's by-reference side effects -> named gradients ->
+    a second model object of the same structure -> finalizer."""
+    r = R(mock_device=True)
+    L = r.L
+    L.psy_mock_live_models.restype = C.c_int
+    model = pd.newPsydiff(**synth.config_c4(N=6, T=8))
+    h = _compile(r, model)
+    assert L.psy_mock_live_models() == 1
+    rm = _r_model(r, model)
+    settings = (r.num([model["alpha"], model["beta"], model["kappa"]]), r.int([0]), r.num(model["timeStep"]), r.lgl(True))
+    theta = r.call("_psydiff_getParameterValues", rm)
+    with pytest.raises(RuntimeError, match="psy_upload|psy_set_slots"):
+        r.call("R_psy_fit", h, rm, *settings, theta, r.lgl(False))
+    assert _sync(r, h, rm, model) is True and _sync(r, h, rm, model) is False
+    obs = model["data"]["observations"]
+    th = model["pars"]["parameterTable"].theta_values
+    want = np.nansum(obs) + np.arange(6) + th.sum()                                    # the mock's arithmetic
+    out = r.py(r.call("R_psy_fit", h, rm, *settings, theta, r.lgl(False)))
+    assert list(out) == ["latentScores", "predictedManifest", "m2LL"] and np.allclose(out["m2LL"], want, rtol=1e-13)
+    assert out["latentScores"].shape == (48, 6) and out["latentScores"][1, 0] == 1001.0 and out["latentScores"][0, 1] == 1048.0   # column-major
+    after = r.py(rm)
+    assert np.array_equal(after["m2LL"], out["m2LL"]) and np.array_equal(after["predictedManifest"], out["predictedManifest"])
+    assert not after["pars"]["parameterTable"]["changed"].any()
+    assert np.all(r.py(r.call("R_psy_fit", h, rm, *settings, theta, r.lgl(True)))["m2LL"] == 0.0)       # skipUpdate reaches the library
+    gr = r.call("R_psy_gradients", h, *settings, theta, r.num(model["eps"]), r.int([2]))
+    assert r.names(gr) == model["pars"]["parameterTable"].theta_labels
+    assert np.allclose(r.py(gr), 2 * th + 6 + 0.002 + model["eps"][0])
+    one = r.call("R_psy_gradient", h, *settings, theta, r.int([4]), r.num(model["eps"]), r.int([2]))
+    assert r.py(one)[0] == r.py(gr)[4] and r.names(one) == [model["pars"]["parameterTable"].theta_labels[4]]
+    with pytest.raises(RuntimeError, match="Unknown direction"):
+        r.call("R_psy_gradients", h, *settings, theta, r.num(model["eps"]), r.int([7]))
+    with pytest.raises(RuntimeError, match="parameter index out of range"):
+        r.call("R_psy_gradient", h, *settings, theta, r.int([999]), r.num(model["eps"]), r.int([0]))
+    # a different model object of the same structure: re-upload, results follow the new data; handing the first one back re-uploads again
+    model2 = pd.newPsydiff(**synth.config_c4(N=4, T=6, seed=77))
+    rm2 = _r_model(r, model2)
+    assert _sync(r, h, rm2, model2) is True
+    out2 = r.py(r.call("R_psy_fit", h, rm2, *settings, r.call("_psydiff_getParameterValues", rm2), r.lgl(False)))
+    assert np.allclose(out2["m2LL"], np.nansum(model2["data"]["observations"]) + np.arange(4) + model2["pars"]["parameterTable"].theta_values.sum(), rtol=1e-13)
+    assert _sync(r, h, rm, model) is True and _sync(r, h, rm, model) is False
+    r.L.psy_rstub_run_finalizer(h)
+    assert L.psy_mock_live_models() == 0 and not r.L.R_ExternalPtrAddr(h)
+    with pytest.raises(RuntimeError, match="model is not compiled"):
+        r.call("R_psy_is_current", h, r.num([0.0]), r.num([0.0]), r.num([0.0]), r.chr(["a"]))
 
 
 @pytest.mark.gpu
