@@ -236,3 +236,30 @@ def test_operator_surface_of_the_equation_language(settings):
     hs, _, _ = _check_fit(model)
     if not settings:
         _check_grad(model, hs, extended=True)
+
+
+def test_kernel_source_under_bounds_and_overflow_sanitizers():
+    """compute-sanitizer is closed on the GPU pool; the kernel source compiled for the host runs under UBSan
+    instead: every fixed-size array index (packed-triangular tri(i, j), slot arrays, the Vec/Mat of the equation language),
+    signed overflow, shifts and null dereferences are checked while the filter runs for n = 2, 6, 8, 10, both steppers and both
+    update variants, fit and gradient sweeps.  Runs in a subprocess: a finding aborts the process."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = f"""
+import sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})
+import numpy as np
+import psydiff_b200 as pd
+from psydiff_b200 import synth
+from hostsim.hostsim import HostSim
+flags = "-fsanitize=bounds,signed-integer-overflow,shift,vla-bound,null -fno-sanitize-recover=all -O1"
+for kw in (synth.config_c1(N=4, T=6, missing=0.3), synth.config_c4(N=3, T=5), synth.config_c3(N=3, T=5), synth.config_c4(N=2, T=4, srUpdate=False),
+           synth.config_coupled(K=4, N=2, T=4), synth.config_coupled(K=5, N=2, T=3)):
+    hs = HostSim(pd.newPsydiff(**kw), flags)
+    assert np.isfinite(hs.fit()["m2LL"]).all() and np.isfinite(hs.gradients()["grad"]).all()
+    assert np.isfinite(hs.fit_many(np.stack([hs.theta(), hs.theta() * 1.01]))).all()
+print("SANITIZER-CLEAN")
+"""
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "SANITIZER-CLEAN" in r.stdout and "runtime error" not in r.stderr, r.stderr[-3000:]
