@@ -238,6 +238,29 @@ def test_operator_surface_of_the_equation_language(settings):
         _check_grad(model, hs, extended=True)
 
 
+def _sanitizer_script(flags):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return f"""
+import sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})
+import numpy as np
+import psydiff_b200 as pd
+from psydiff_b200 import synth
+from hostsim.hostsim import HostSim
+flags = {flags!r}
+ragged = synth.config_c1(N=5, T=7, missing=0.3)
+keep = np.ones(35, dtype=bool); keep[7 + 1:14] = False; keep[30:35] = False          # a single-row person, a shorter last person
+ragged["dataset"] = {{k: v[keep] for k, v in ragged["dataset"].items()}}
+for kw in (ragged, synth.config_c4(N=3, T=5), synth.config_c3(N=3, T=5), synth.config_c4(N=2, T=4, srUpdate=False),
+           synth.config_coupled(K=4, N=2, T=4), synth.config_coupled(K=5, N=2, T=3)):
+    hs = HostSim(pd.newPsydiff(**kw), flags)
+    assert np.isfinite(hs.fit()["m2LL"]).all() and np.isfinite(hs.gradients()["grad"]).all()
+    assert np.isfinite(hs.gradients(pad=False)["grad"]).all()
+    assert np.isfinite(hs.fit_many(np.stack([hs.theta(), hs.theta() * 1.01]))).all()
+print("SANITIZER-CLEAN")
+"""
+
+
 def test_kernel_source_under_bounds_and_overflow_sanitizers():
     """compute-sanitizer is closed on the GPU pool; the kernel source compiled for the host runs under UBSan
     instead: every fixed-size array index (packed-triangular tri(i, j), slot arrays, the Vec/Mat of the equation language),
@@ -245,21 +268,20 @@ def test_kernel_source_under_bounds_and_overflow_sanitizers():
     update variants, fit and gradient sweeps.  Runs in a subprocess: a finding aborts the process."""
     import subprocess
     import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    script = f"""
-import sys
-sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})
-import numpy as np
-import psydiff_b200 as pd
-from psydiff_b200 import synth
-from hostsim.hostsim import HostSim
-flags = "-fsanitize=bounds,signed-integer-overflow,shift,vla-bound,null -fno-sanitize-recover=all -O1"
-for kw in (synth.config_c1(N=4, T=6, missing=0.3), synth.config_c4(N=3, T=5), synth.config_c3(N=3, T=5), synth.config_c4(N=2, T=4, srUpdate=False),
-           synth.config_coupled(K=4, N=2, T=4), synth.config_coupled(K=5, N=2, T=3)):
-    hs = HostSim(pd.newPsydiff(**kw), flags)
-    assert np.isfinite(hs.fit()["m2LL"]).all() and np.isfinite(hs.gradients()["grad"]).all()
-    assert np.isfinite(hs.fit_many(np.stack([hs.theta(), hs.theta() * 1.01]))).all()
-print("SANITIZER-CLEAN")
-"""
-    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([sys.executable, "-c", _sanitizer_script("-fsanitize=bounds,signed-integer-overflow,shift,vla-bound,null -fno-sanitize-recover=all -O1")],
+                       capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "SANITIZER-CLEAN" in r.stdout and "runtime error" not in r.stderr, r.stderr[-3000:]
+
+
+def test_kernel_source_under_address_sanitizer():
+    """The same runs under AddressSanitizer: every access the kernel makes into the launch buffers (observation rows, dt, step
+    counts, row offsets, slot map, theta sets, instance list incl. padding slots, -2LL / state outputs) stays inside them."""
+    import subprocess
+    import sys
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not available")
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([sys.executable, "-c", _sanitizer_script("-fsanitize=address -fno-omit-frame-pointer -O1")],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "SANITIZER-CLEAN" in r.stdout and "AddressSanitizer" not in r.stderr, r.stderr[-3000:]
