@@ -385,3 +385,20 @@ def test_unknown_direction_is_an_error():
     model = pd.newPsydiff(**synth.config_c1(N=3, T=5, direction="sideways"))
     with pytest.raises(RuntimeError, match="Unknown direction argument. Possible are central, left and right"):
         rb.Reference(model).gradients()
+
+
+@pytest.mark.parametrize("stepper", ["rk4", "runge_kutta_dopri5"])
+def test_odd_time_intervals(stepper):
+    """dt < 0 (nothing is integrated: the loops' conditions fail), dt below DBL_EPSILON, dt below the step size (zero RK4 steps),
+    an exact multiple of the step, 1 + 1e-16: reference, oracle and kernel source agree."""
+    from hostsim.hostsim import HostSim
+    kw = synth.config_c1(N=4, T=8, seed=3, integrateFunction=stepper)
+    dt = kw["dataset"]["dt"].copy()
+    dt[2], dt[3], dt[5], dt[10], dt[12], dt[13] = -0.5, 1e-17, 1e-3, 1.0 + 1e-16, 3 * (1 / 30), 0.1
+    kw["dataset"]["dt"] = dt
+    kw["timeStep"] = np.array([1 / 30])
+    model = pd.newPsydiff(**kw)
+    ref, orc, _ = _fit_pair(model)
+    ker = HostSim(model).fit()
+    assert np.max(np.abs(ker["m2LL"] - ref["m2LL"]) / np.abs(ref["m2LL"])) < M2LL_RTOL
+    assert np.nanmax(np.abs(ker["latentScores"] - ref["latentScores"])) < 1e-9
