@@ -429,3 +429,18 @@ def test_accuracy_of_reference_and_kernel_as_alpha_shrinks():
     # below that the reference breaks down entirely, the kernel still returns finite values
     model = pd.newPsydiff(**synth.config_c4(N=2, T=6, alpha=0.005, breakEarly=False))
     assert not np.isfinite(rb.Reference(model).fit()["m2LL"]).any() and np.isfinite(HostSim(model).fit()["m2LL"]).all()
+
+
+@pytest.mark.parametrize("sr", [True, False], ids=["sr", "cov"])
+def test_ill_conditioned_noise_levels(sr):
+    """Small measurement noise / diffusion (condition number of S up to ~1e6): reference, oracle and kernel source still agree
+    within the gate, and the kernel is at least as close to the 80-bit value as the reference's own code is."""
+    from hostsim.hostsim import HostSim
+    for rs, ls in ((1e-2, np.sqrt(.5)), (np.sqrt(.5), 1e-2), (1e-3, 2e-2)):
+        kw = synth.config_c1(N=3, T=12, breakEarly=False, srUpdate=sr, Rchol=np.diag([rs, rs]), L=np.diag([ls, ls]), sanityChecks=False)
+        model = pd.newPsydiff(**kw)
+        ref, _, _ = _fit_pair(model)
+        ext = _oracle(model, extended=True).fit()["m2LL"]
+        ker = HostSim(model).fit()["m2LL"]
+        e_ref, e_ker = np.max(np.abs(ref["m2LL"] - ext) / np.abs(ext)), np.max(np.abs(ker - ext) / np.abs(ext))
+        assert e_ker <= max(e_ref, 1e-13) and e_ker < 1e-9, (rs, ls, e_ref, e_ker)
