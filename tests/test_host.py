@@ -507,3 +507,60 @@ def test_product_code_never_touches_the_checkers():
     # the one hook the kernel header has for the host compile is inert on the device
     hdr = open(os.path.join(pkg, "csrc", "psy_filter.cuh")).read()
     assert "#ifdef __CUDA_ARCH__" in hdr and hdr.count("psy_sim_rcp_seed") == 1
+
+
+def test_r_wrapper_file_is_lexically_well_formed_and_binds_registered_routines():
+    """r/psydiff_b200.R cannot be executed here (no R): at least its brackets and strings balance, and every routine it .Call()s
+    is registered by the shim with the number of arguments the call passes."""
+    text = open(os.path.join(ROOT, "r", "psydiff_b200.R")).read()
+    stack, i, n = [], 0, len(text)
+    pairs = {")": "(", "]": "[", "}": "{"}
+    while i < n:
+        ch = text[i]
+        if ch == "#":
+            while i < n and text[i] != "\n":
+                i += 1
+            continue
+        if ch in "\"'":
+            q = ch
+            i += 1
+            while i < n and text[i] != q:
+                i += 2 if text[i] == "\\" else 1
+            assert i < n, "unterminated string"
+        elif ch in "([{":
+            stack.append(ch)
+        elif ch in ")]}":
+            assert stack and stack.pop() == pairs[ch], f"unbalanced {ch} at offset {i}"
+        i += 1
+    assert not stack
+    shim = open(os.path.join(ROOT, "r", "psydiff_b200_shim.c")).read()
+    registered = {m.group(1): int(m.group(2)) for m in re.finditer(r'\{"(\w+)", \(DL_FUNC\)&\w+, (\d+)\}', shim)}
+
+    def count_args(s, start):                         # arguments of the call whose "(" is at s[start]
+        depth, args, j, seen = 0, 0, start, False
+        while j < len(s):
+            c = s[j]
+            if c in "\"'":
+                q = c
+                j += 1
+                while s[j] != q:
+                    j += 2 if s[j] == "\\" else 1
+            elif c in "([{":
+                depth += 1
+            elif c in ")]}":
+                depth -= 1
+                if depth == 0:
+                    return args + (1 if seen else 0)
+            elif c == "," and depth == 1:
+                args += 1
+            elif depth >= 1 and not c.isspace():
+                seen = True
+            j += 1
+        raise AssertionError("unterminated call")
+
+    code = "\n".join(l.split("#")[0] for l in text.splitlines())
+    calls = [(m.group(1), count_args(code, m.start(0) + len(".Call"))) for m in re.finditer(r'\.Call\("(\w+)"', code) if "..." not in code[m.start(0):m.start(0) + 80]]
+    assert {c for c, _ in calls} >= {"R_psy_emit_source", "R_psy_compile", "R_psy_is_current", "R_psy_upload", "R_psy_fit", "R_psy_gradients", "R_psy_gradient"}
+    for name, nargs in calls:
+        assert name in registered, name
+        assert nargs - 1 == registered[name], (name, nargs - 1, registered[name])      # the first argument is the routine's name
