@@ -84,5 +84,23 @@ inline ol::Vec log(const ol::Vec& a) { ol::Vec r(a.n()); for (int i = 0; i < a.n
 inline real dot(const ol::Vec& a, const ol::Vec& b) { real s = 0; for (int i = 0; i < a.n(); i++) s += a.v[i] * b.v[i]; return s; }
 inline real accu(const ol::Vec& a) { real s = 0; for (int i = 0; i < a.n(); i++) s += a.v[i]; return s; }
 inline real sum(const ol::Vec& a) { return accu(a); }
+typedef ol::Mat mat;       // initialised temporaries the user declares: `arma::mat T = arma::expm(A);`
+typedef ol::Vec colvec;
+typedef ol::Vec vec;
+// arma::expm: scaling and squaring around a degree-12 Taylor polynomial (third-party arithmetic, restated; Armadillo uses Pade)
+inline ol::Mat expm(const ol::Mat& A) {
+  const int n = A.r;
+  real nrm = 0;
+  for (int j = 0; j < n; j++) { real cs = 0; for (int i = 0; i < n; i++) cs += std::fabs(A(i, j)); nrm = cs > nrm ? cs : nrm; }
+  int s = 0;
+  real sc = 1.0;
+  while (nrm * sc > 0.5 && s < 64) { sc *= 0.5; s++; }
+  const ol::Mat B = sc * A;
+  ol::Mat E(n, n);
+  for (int i = 0; i < n; i++) E(i, i) = 1.0;
+  for (int k = 12; k >= 1; k--) { E = ((real)1.0 / (real)k) * (B * E); for (int i = 0; i < n; i++) E(i, i) += 1.0; }
+  for (int q = 0; q < s; q++) E = E * E;
+  return E;
+}
 inline ol::Mat trans(const ol::Mat& a) { ol::Mat r(a.c, a.r); for (int j = 0; j < a.c; j++) for (int i = 0; i < a.r; i++) r(j, i) = a(i, j); return r; }
 }  // namespace arma

@@ -189,6 +189,17 @@ inline uvec operator==(const Mat& a, double s) { uvec u; for (double x : a.mem) 
 
 inline Mat trans(const Mat& a) { Mat r(a.n_cols, a.n_rows); for (uword j = 0; j < a.n_cols; j++) for (uword i = 0; i < a.n_rows; i++) r(j, i) = a(i, j); return r; }
 inline Mat eye(uword r, uword c) { Mat m(r, c); for (uword i = 0; i < std::min(r, c); i++) m(i, i) = 1.0; return m; }
+inline Mat expm(const Mat& A) {  // scaling and squaring, degree-12 Taylor (Armadillo: Pade; both accurate to rounding)
+  if (A.n_rows != A.n_cols) throw std::logic_error("expm(): given matrix must be square sized");
+  const uword n = A.n_rows; double nrm = 0.0;
+  for (uword j = 0; j < n; j++) { double cs = 0.0; for (uword i = 0; i < n; i++) cs += std::fabs(A(i, j)); nrm = std::max(nrm, cs); }
+  int s = 0; double sc = 1.0;
+  while (nrm * sc > 0.5 && s < 64) { sc *= 0.5; s++; }
+  Mat B = sc * A, E = eye(n, n);
+  for (int k = 12; k >= 1; k--) { E = (1.0 / k) * (B * E); for (uword i = 0; i < n; i++) E(i, i) += 1.0; }
+  for (int q = 0; q < s; q++) E = E * E;
+  return E;
+}
 inline Mat diagmat(const Mat& v) { Mat m(v.n_elem, v.n_elem); for (uword i = 0; i < v.n_elem; i++) m(i, i) = v.mem[i]; return m; }
 inline Mat log(const Mat& a) { Mat r = a; for (auto& x : r.mem) x = std::log(x); return r; }
 inline Mat exp(const Mat& a) { Mat r = a; for (auto& x : r.mem) x = std::exp(x); return r; }

@@ -136,11 +136,18 @@ std::string indent_statements(const std::string& eq) {
   return out + "\n";
 }
 
+// Initialised Armadillo temporaries (`arma::mat T = arma::expm(A);`, vignettes/psydiff-basics.Rmd:94-98) get the type of their
+// initialiser: on the device every matrix has compile-time extents, so the declared type becomes `auto`.
+std::string device_statements(const std::string& eq) {
+  static const std::regex typed(R"(\barma\s*::\s*(?:mat|colvec|vec|rowvec)\s+([A-Za-z_][A-Za-z0-9_]*)\s*=(?!=))");
+  return std::regex_replace(eq, typed, "auto $1 =");
+}
+
 // prepareEquations (R/prepareModel.R:737-770): declarations of the containers the text names, then the statements
 std::string prepare_equations(const std::string& eq, const std::vector<Cont>& cs) {
   std::string out;
   for (auto* c : referenced(eq, cs)) out += bind(*c);
-  return out + indent_statements(eq);
+  return out + indent_statements(device_statements(eq));
 }
 
 std::string strip(const std::string& s) {

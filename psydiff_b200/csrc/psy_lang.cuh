@@ -8,9 +8,11 @@
 //
 // Supported surface: x(i) / x[i] element access on vectors, M(i,j) on matrices, + - * between matrices, vectors
 // and scalars (matrix*vector, matrix*matrix, scalar scaling), element-wise % and /, unary minus, assignment of a
-// scalar to a 1-vector (`y = x(0);`), arma::exp/log/trans/dot/accu, and every CUDA <cmath> function on scalars.
-// Anything else (arma::expm, dynamic-size temporaries declared as arma::mat/colvec) does not compile and is
-// reported by compileModel as "unsupported on device".
+// scalar to a 1-vector (`y = x(0);`), arma::exp/log/trans/dot/accu, arma::expm of a square matrix (the vignette's example,
+// vignettes/psydiff-basics.Rmd:94-98), and every CUDA <cmath> function on scalars.  Initialised temporaries
+// `arma::mat T = <expr>;` / `arma::colvec v = <expr>;` are accepted: the code generator turns the declared type into `auto`,
+// so T gets the expression's compile-time extents.  Anything else (size-only declarations such as `arma::mat T(2,2);`,
+// other Armadillo functions) does not compile and is reported by compileModel as "unsupported on device".
 #pragma once
 
 namespace psy {
@@ -219,6 +221,35 @@ __device__ __forceinline__ double accu(const psy::Vec<N>& a) {
 }
 template <int N>
 __device__ __forceinline__ double sum(const psy::Vec<N>& a) { return accu(a); }
+// arma::expm: scaling and squaring around a degree-12 Taylor polynomial in Horner form.  ||A / 2^s||_1 <= 1/2 makes the
+// truncation error < 2e-14 relative; Armadillo's Pade-based expm agrees with it to rounding.
+template <int N>
+__device__ __forceinline__ psy::Mat<N, N> expm(const psy::Mat<N, N>& A) {
+  double nrm = 0.0;
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    double cs = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; i++) cs += fabs(A.a[i + j * N]);
+    nrm = fmax(nrm, cs);
+  }
+  int s = 0;
+  double sc = 1.0;
+  while (nrm * sc > 0.5 && s < 64) { sc *= 0.5; s++; }
+  const psy::Mat<N, N> B = sc * A;
+  psy::Mat<N, N> E;
+#pragma unroll
+  for (int i = 0; i < N * N; i++) E.a[i] = (i % (N + 1) == 0) ? 1.0 : 0.0;
+#pragma unroll 1
+  for (int k = 12; k >= 1; k--) {
+    E = (1.0 / (double)k) * (B * E);
+#pragma unroll
+    for (int i = 0; i < N; i++) E.a[i + i * N] += 1.0;
+  }
+#pragma unroll 1
+  for (int q = 0; q < s; q++) E = E * E;
+  return E;
+}
 template <int R, int C>
 __device__ __forceinline__ psy::Mat<C, R> trans(const psy::Mat<R, C>& a) {
   psy::Mat<C, R> r;

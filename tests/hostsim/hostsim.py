@@ -93,7 +93,6 @@ class HostSim:
         spec = model["_spec"]
         self.n, self.m, self.F = spec.nlatent, spec.nmanifest, spec.n_slots
         pt = model["pars"]["parameterTable"]
-        self.tidx = np.ascontiguousarray(pt.theta_index, dtype=np.int32).reshape(-1, max(self.F, 1) if self.F else 0)
         self.P = len(pt.theta_labels)
         self.row_off = np.ascontiguousarray(model["_row_off"], dtype=np.int64)
         self.obs = np.ascontiguousarray(model["data"]["observations"], dtype=np.float64)   # [rows][m] row-major
@@ -101,6 +100,7 @@ class HostSim:
         self.pid = np.ascontiguousarray(np.asarray(model["_persons_unique"], dtype=np.float64).astype(np.int32))
         self.N = len(self.pid)
         self.rows = int(self.row_off[-1])
+        self.tidx = np.ascontiguousarray(pt.theta_index, dtype=np.int32).reshape(self.N, self.F)   # N x 0 for a model without free parameters
         self._rk = _lib.lib().psy_rk4_step_count          # host-only exported helper of the C ABI (rule T1)
         self._rk.argtypes, self._rk.restype = [C.c_double, C.c_double], C.c_int
 
@@ -140,6 +140,8 @@ class HostSim:
         ks = np.array([self._rk(float(d), h) for d in self.dt], dtype=np.int32)
         f = np.full(n_inst, np.nan)
         th = np.ascontiguousarray(thetas, dtype=np.float64)
+        if th.size == 0:
+            th = np.zeros(1)                               # the library allocates max(P, 1) doubles as well
         L = PsyLaunch()
         L.obs, L.dt, L.ksteps, L.row_off = _ptr(self.obs), _ptr(self.dt), _ptr(ks), _ptr(self.row_off)
         L.person_id, L.theta_index, L.theta = _ptr(self.pid), _ptr(self.tidx), _ptr(th)
@@ -170,7 +172,8 @@ class HostSim:
 
     def fit_many(self, thetas, skip_update=False):
         """psy_fit_many: set-major blocks of persons, code = -1 - set."""
-        thetas = np.ascontiguousarray(thetas, dtype=np.float64).reshape(-1, max(self.P, 1))
+        thetas = np.ascontiguousarray(thetas, dtype=np.float64)
+        thetas = thetas.reshape(-1, self.P) if self.P else np.zeros((max(len(thetas), 1), 1))
         k = thetas.shape[0]
         inst = (PsyInst * (self.N * k))(*[PsyInst(p, -1 - s) for s in range(k) for p in range(self.N)])
         f = self._launch(inst, self.N * k, thetas, 0.0, skip_update).reshape(k, self.N)

@@ -564,3 +564,18 @@ def test_r_wrapper_file_is_lexically_well_formed_and_binds_registered_routines()
     for name, nargs in calls:
         assert name in registered, name
         assert nargs - 1 == registered[name], (name, nargs - 1, registered[name])      # the first argument is the routine's name
+
+
+def test_typed_temporaries_and_expm_compile_for_the_device():
+    from test_kernel_hostsim import vignette_expm_model
+    m = pd.newPsydiff(**vignette_expm_model())
+    assert m["cppCode"] == codegen.emit_cuda_py(m["_spec"])                   # both generators rewrite the declarations alike
+    assert codegen.drift_dependency(m["_spec"]) == [3, 3]                     # temporaries: the sparsity analysis gives up (all ones)
+    cubin = pd.compileModelSource(m)
+    assert os.path.getsize(cubin) > 1000
+    got = codegen.device_statements("arma :: colvec v=x; arma::mat T = A*B; if (a == b) arma::vec w = v;")
+    assert got == "auto v =x; auto T = A*B; if (a == b) auto w = v;"
+    bad = dict(vignette_expm_model())
+    bad["latentEquations"] = "arma::mat T(2, 2);\n" + bad["latentEquations"]   # a size-only declaration has no device counterpart
+    with pytest.raises(PsydiffError, match="unsupported on device"):
+        pd.compileModelSource(pd.newPsydiff(**bad))

@@ -285,3 +285,37 @@ def test_kernel_source_under_address_sanitizer():
     r = subprocess.run([sys.executable, "-c", _sanitizer_script("-fsanitize=address -fno-omit-frame-pointer -O1")],
                        capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0 and "SANITIZER-CLEAN" in r.stdout and "AddressSanitizer" not in r.stderr, r.stderr[-3000:]
+
+
+def vignette_expm_model(use_expm=True, free=True):
+    """The vignette's "quite complex models" example (vignettes/psydiff-basics.Rmd:94-98): a typed Armadillo temporary holding the
+    matrix exponential of a parameter matrix, here actually used in the drift.  use_expm=False supplies scipy's expm(A) as a
+    constant matrix instead; free=False fixes every parameter (a model without free parameters)."""
+    import scipy.linalg
+    rng = np.random.default_rng(3)
+    N, T = 4, 8
+    ds = {"person": np.repeat(np.arange(1, N + 1), T), "observations": rng.standard_normal((N * T, 2)),
+          "dt": np.tile(np.r_[0.0, np.full(T - 1, 0.5)], N)}
+    A = np.array([[-0.4, 0.3], [0.1, -0.7]])
+    common = dict(dataset=ds, manifestEquations="y = x;", L=np.diag([0.5, 0.4]), Rchol=np.diag([0.6, 0.5]), A0=np.diag([0.8, 0.7]),
+                  m0=np.array([[1.0], [0.5]]), integrateFunction="rk4", eps=np.array([1e-6]), timeStep=np.array([1 / 20]))
+    tail = "arma::colvec z = expOfA*x;\ndx[0] = -z[0] + 0.1*x[1];\ndx[1] = -0.5*z[1];"
+    if use_expm:
+        Apar = np.array([["a11 = -0.4", "0.3"], ["0.1", "a22 = -0.7"]], dtype=object) if free else A
+        return dict(latentEquations="arma::mat expOfA = arma::expm(A);\n" + tail, parameters={"A": Apar}, **common)
+    return dict(latentEquations=tail, parameters={"expOfA": scipy.linalg.expm(A)}, **common)
+
+
+def test_vignette_expm_and_typed_temporaries():
+    model = pd.newPsydiff(**vignette_expm_model())
+    assert "auto expOfA = arma::expm(A);" in model["cppCode"] and "auto z = expOfA*x;" in model["cppCode"]
+    hs, fit, _ = _check_fit(model)
+    _check_grad(model, hs, extended=True)
+    # the matrix exponential itself: the same filter with scipy's expm(A) supplied as a constant
+    const = pd.newPsydiff(**vignette_expm_model(use_expm=False))
+    assert len(const["pars"]["parameterTable"].theta_labels) == 0            # ... which is also a model without free parameters
+    ref = HostSim(const).fit()
+    assert np.max(np.abs(fit["m2LL"] - ref["m2LL"]) / np.abs(ref["m2LL"])) < 1e-13
+    assert HostSim(const).gradients()["grad"].shape == (0,)
+    fixed = pd.newPsydiff(**vignette_expm_model(free=False))
+    assert np.array_equal(HostSim(fixed).fit()["m2LL"], fit["m2LL"])         # fixing the parameters at their values changes nothing

@@ -444,3 +444,10 @@ def test_ill_conditioned_noise_levels(sr):
         ker = HostSim(model).fit()["m2LL"]
         e_ref, e_ker = np.max(np.abs(ref["m2LL"] - ext) / np.abs(ext)), np.max(np.abs(ker - ext) / np.abs(ext))
         assert e_ker <= max(e_ref, 1e-13) and e_ker < 1e-9, (rs, ls, e_ref, e_ker)
+
+
+def test_vignette_expm_example():
+    """vignettes/psydiff-basics.Rmd:94-98: `arma::mat expOfA = arma::expm(A);` in the latent equation, through the reference's code
+    (the stand-in's expm and the oracle's are the same scaling-and-squaring restatement; the kernel test checks it against scipy)."""
+    from test_kernel_hostsim import vignette_expm_model
+    _fit_pair(pd.newPsydiff(**vignette_expm_model()))
