@@ -81,6 +81,22 @@ inline Mat operator*(const Mat& A, const Mat& B) {
 namespace arma {
 inline ol::Vec exp(const ol::Vec& a) { ol::Vec r(a.n()); for (int i = 0; i < a.n(); i++) r.v[i] = std::exp(a.v[i]); return r; }
 inline ol::Vec log(const ol::Vec& a) { ol::Vec r(a.n()); for (int i = 0; i < a.n(); i++) r.v[i] = std::log(a.v[i]); return r; }
+#define OL_ELEMENTWISE(NAME, EXPR) \
+  inline ol::Vec NAME(const ol::Vec& a) { ol::Vec r(a.n()); for (int i = 0; i < a.n(); i++) { const real v = a.v[i]; r.v[i] = (EXPR); } return r; }
+OL_ELEMENTWISE(sin, std::sin(v))
+OL_ELEMENTWISE(cos, std::cos(v))
+OL_ELEMENTWISE(tanh, std::tanh(v))
+OL_ELEMENTWISE(sqrt, std::sqrt(v))
+OL_ELEMENTWISE(abs, std::fabs(v))
+OL_ELEMENTWISE(square, v * v)
+#undef OL_ELEMENTWISE
+inline ol::Vec pow(const ol::Vec& a, real p) { ol::Vec r(a.n()); for (int i = 0; i < a.n(); i++) r.v[i] = std::pow(a.v[i], p); return r; }
+inline real norm(const ol::Vec& a) { real s = 0; for (int i = 0; i < a.n(); i++) s += a.v[i] * a.v[i]; return std::sqrt(s); }
+inline real max(const ol::Vec& a) { real m = a.v[0]; for (int i = 1; i < a.n(); i++) m = a.v[i] > m ? a.v[i] : m; return m; }
+inline real min(const ol::Vec& a) { real m = a.v[0]; for (int i = 1; i < a.n(); i++) m = a.v[i] < m ? a.v[i] : m; return m; }
+inline real mean(const ol::Vec& a) { real s = 0; for (int i = 0; i < a.n(); i++) s += a.v[i]; return s / (real)a.n(); }
+inline real as_scalar(const ol::Vec& a) { return a.v[0]; }
+inline real as_scalar(const ol::Mat& a) { return a.a[0]; }
 inline real dot(const ol::Vec& a, const ol::Vec& b) { real s = 0; for (int i = 0; i < a.n(); i++) s += a.v[i] * b.v[i]; return s; }
 inline real accu(const ol::Vec& a) { real s = 0; for (int i = 0; i < a.n(); i++) s += a.v[i]; return s; }
 inline real sum(const ol::Vec& a) { return accu(a); }

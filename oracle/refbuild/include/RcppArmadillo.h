@@ -203,6 +203,20 @@ inline Mat expm(const Mat& A) {  // scaling and squaring, degree-12 Taylor (Arma
 inline Mat diagmat(const Mat& v) { Mat m(v.n_elem, v.n_elem); for (uword i = 0; i < v.n_elem; i++) m(i, i) = v.mem[i]; return m; }
 inline Mat log(const Mat& a) { Mat r = a; for (auto& x : r.mem) x = std::log(x); return r; }
 inline Mat exp(const Mat& a) { Mat r = a; for (auto& x : r.mem) x = std::exp(x); return r; }
+#define PSY_REF_ELEMENTWISE(NAME, EXPR) inline Mat NAME(const Mat& a) { Mat r = a; for (auto& v : r.mem) v = (EXPR); return r; }
+PSY_REF_ELEMENTWISE(sin, std::sin(v))
+PSY_REF_ELEMENTWISE(cos, std::cos(v))
+PSY_REF_ELEMENTWISE(tanh, std::tanh(v))
+PSY_REF_ELEMENTWISE(sqrt, std::sqrt(v))
+PSY_REF_ELEMENTWISE(abs, std::fabs(v))
+PSY_REF_ELEMENTWISE(square, v * v)
+#undef PSY_REF_ELEMENTWISE
+inline Mat pow(const Mat& a, double p) { Mat r = a; for (auto& v : r.mem) v = std::pow(v, p); return r; }
+inline double norm(const Mat& a) { double s = 0.0; for (double x : a.mem) s += x * x; return std::sqrt(s); }   // vectors (2-norm)
+inline double max(const Mat& a) { if (a.mem.empty()) throw std::logic_error("max(): object has no elements"); return *std::max_element(a.mem.begin(), a.mem.end()); }
+inline double min(const Mat& a) { if (a.mem.empty()) throw std::logic_error("min(): object has no elements"); return *std::min_element(a.mem.begin(), a.mem.end()); }
+inline double mean(const Mat& a) { double s = 0.0; for (double x : a.mem) s += x; return s / (double)a.n_elem; }   // vectors
+inline double as_scalar(const Mat& a) { if (a.n_elem != 1) throw std::logic_error("as_scalar(): expression must evaluate to exactly one element"); return a.mem[0]; }
 inline double accu(const Mat& a) { double s = 0.0; for (double x : a.mem) s += x; return s; }
 inline double dot(const Mat& a, const Mat& b) { if (a.n_elem != b.n_elem) throw std::logic_error("dot(): objects must have the same number of elements"); double s = 0.0; for (uword k = 0; k < a.n_elem; k++) s += a.mem[k] * b.mem[k]; return s; }
 inline double sum(const Mat& a) { double s = 0.0; for (double x : a.mem) s += x; return s; }  // vectors only (all the reference uses)

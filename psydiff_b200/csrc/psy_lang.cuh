@@ -8,7 +8,8 @@
 //
 // Supported surface: x(i) / x[i] element access on vectors, M(i,j) on matrices, + - * between matrices, vectors
 // and scalars (matrix*vector, matrix*matrix, scalar scaling), element-wise % and /, unary minus, assignment of a
-// scalar to a 1-vector (`y = x(0);`), arma::exp/log/trans/dot/accu, arma::expm of a square matrix (the vignette's example,
+// scalar to a 1-vector (`y = x(0);`), arma::exp/log/sin/cos/tanh/sqrt/abs/square/pow on vectors, arma::dot/accu/sum/mean/norm/max/
+// min/as_scalar/trans, arma::expm of a square matrix (the vignette's example,
 // vignettes/psydiff-basics.Rmd:94-98), and every CUDA <cmath> function on scalars.  Initialised temporaries
 // `arma::mat T = <expr>;` / `arma::colvec v = <expr>;` are accepted: the code generator turns the declared type into `auto`,
 // so T gets the expression's compile-time extents.  Anything else (size-only declarations such as `arma::mat T(2,2);`,
@@ -205,6 +206,59 @@ __device__ __forceinline__ psy::Vec<N> log(const psy::Vec<N>& a) {
   for (int i = 0; i < N; i++) r.v[i] = ::log(a.v[i]);
   return r;
 }
+// element-wise <cmath> functions on vectors: arma::sin(x), arma::tanh(x), arma::sqrt(x), arma::abs(x), arma::square(x), arma::pow(x, p)
+#define PSY_ARMA_ELEMENTWISE(NAME, EXPR)                                       \
+  template <int N>                                                             \
+  __device__ __forceinline__ psy::Vec<N> NAME(const psy::Vec<N>& a) {          \
+    psy::Vec<N> r;                                                             \
+    _Pragma("unroll") for (int i = 0; i < N; i++) { const double v = a.v[i]; r.v[i] = (EXPR); } \
+    return r;                                                                  \
+  }
+PSY_ARMA_ELEMENTWISE(sin, ::sin(v))
+PSY_ARMA_ELEMENTWISE(cos, ::cos(v))
+PSY_ARMA_ELEMENTWISE(tanh, ::tanh(v))
+PSY_ARMA_ELEMENTWISE(sqrt, ::sqrt(v))
+PSY_ARMA_ELEMENTWISE(abs, ::fabs(v))
+PSY_ARMA_ELEMENTWISE(square, v * v)
+#undef PSY_ARMA_ELEMENTWISE
+template <int N>
+__device__ __forceinline__ psy::Vec<N> pow(const psy::Vec<N>& a, double p) {
+  psy::Vec<N> r;
+#pragma unroll
+  for (int i = 0; i < N; i++) r.v[i] = ::pow(a.v[i], p);
+  return r;
+}
+// reductions: arma::norm (2-norm), max, min, mean, as_scalar of a one-element object
+template <int N>
+__device__ __forceinline__ double norm(const psy::Vec<N>& a) {
+  double acc = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) acc += a.v[i] * a.v[i];
+  return ::sqrt(acc);
+}
+template <int N>
+__device__ __forceinline__ double max(const psy::Vec<N>& a) {
+  double m = a.v[0];
+#pragma unroll
+  for (int i = 1; i < N; i++) m = (a.v[i] > m) ? a.v[i] : m;
+  return m;
+}
+template <int N>
+__device__ __forceinline__ double min(const psy::Vec<N>& a) {
+  double m = a.v[0];
+#pragma unroll
+  for (int i = 1; i < N; i++) m = (a.v[i] < m) ? a.v[i] : m;
+  return m;
+}
+template <int N>
+__device__ __forceinline__ double mean(const psy::Vec<N>& a) {
+  double acc = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) acc += a.v[i];
+  return acc / (double)N;
+}
+__device__ __forceinline__ double as_scalar(const psy::Vec<1>& a) { return a.v[0]; }
+__device__ __forceinline__ double as_scalar(const psy::Mat<1, 1>& a) { return a.a[0]; }
 template <int N>
 __device__ __forceinline__ double dot(const psy::Vec<N>& a, const psy::Vec<N>& b) {
   double acc = 0;

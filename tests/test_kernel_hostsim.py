@@ -319,3 +319,21 @@ def test_vignette_expm_and_typed_temporaries():
     assert HostSim(const).gradients()["grad"].shape == (0,)
     fixed = pd.newPsydiff(**vignette_expm_model(free=False))
     assert np.array_equal(HostSim(fixed).fit()["m2LL"], fit["m2LL"])         # fixing the parameters at their values changes nothing
+
+
+def elementwise_functions_model(**settings):
+    """arma::sin / cos / tanh / sqrt / abs / square / pow on vectors, arma::norm / max / min / mean / as_scalar / sum."""
+    kw = operator_surface_model(**settings)
+    kw["latentEquations"] = ("dx = DRIFT*x + CINT;\n"
+                             "dx = dx - 0.05*arma::tanh(x) + 0.02*arma::sin(x) - 0.01*arma::cos(2.0*x);\n"
+                             "dx = dx - 0.01*arma::pow(arma::abs(x), 1.5) - 0.005*arma::square(x);\n"
+                             "dx(0) = dx(0) - 0.01*arma::norm(x) + 0.003*arma::max(x) - 0.002*arma::min(x) + 0.004*arma::mean(x);\n"
+                             "dx(1) = dx(1) + 0.01*arma::as_scalar(arma::trans(CINT)*x) + 0.001*arma::sum(x);")
+    kw["manifestEquations"] = "y = arma::trans(LT)*x + MM;\ny = y + 0.05*arma::sqrt(arma::square(x) + 1.0);"
+    return kw
+
+
+def test_elementwise_and_reduction_functions_of_the_equation_language():
+    model = pd.newPsydiff(**elementwise_functions_model())
+    hs, _, _ = _check_fit(model)
+    _check_grad(model, hs, extended=True)

@@ -451,3 +451,8 @@ def test_vignette_expm_example():
     (the stand-in's expm and the oracle's are the same scaling-and-squaring restatement; the kernel test checks it against scipy)."""
     from test_kernel_hostsim import vignette_expm_model
     _fit_pair(pd.newPsydiff(**vignette_expm_model()))
+
+
+def test_elementwise_and_reduction_functions_of_the_equation_language():
+    from test_kernel_hostsim import elementwise_functions_model
+    _fit_pair(pd.newPsydiff(**elementwise_functions_model()))
