@@ -337,3 +337,26 @@ def test_elementwise_and_reduction_functions_of_the_equation_language():
     model = pd.newPsydiff(**elementwise_functions_model())
     hs, _, _ = _check_fit(model)
     _check_grad(model, hs, extended=True)
+
+
+def control_flow_model():
+    """Plain C++ control flow in the statements: a counted loop over components, if / else on the state, a conditional expression
+    on t, element access M(i, j) with a loop index."""
+    kw = operator_surface_model()
+    kw["latentEquations"] = ("for (int i = 0; i < 2; i++) { dx(i) = DRIFT(i,i)*x(i) + CINT(i); }\n"
+                             "if (x(0) > 0) { dx(0) = dx(0) - 0.1*x(0)*x(0); } else { dx(0) = dx(0) + 0.05*x(1); }\n"
+                             "double damp = (t > 0.3) ? 0.9 : 1.0;\n"
+                             "dx(1) = damp*dx(1) + DRIFT(1,0)*x(0);")
+    kw["manifestEquations"] = "y = arma::trans(LT)*x + MM;"
+    return kw
+
+
+def test_control_flow_in_the_statements():
+    model = pd.newPsydiff(**control_flow_model())
+    assert codegen_dep(model) == [3, 3]                    # not plain element statements: the sparsity analysis gives up
+    _check_fit(model)
+
+
+def codegen_dep(model):
+    from psydiff_b200 import codegen
+    return codegen.drift_dependency(model["_spec"])

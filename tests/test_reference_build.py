@@ -456,3 +456,8 @@ def test_vignette_expm_example():
 def test_elementwise_and_reduction_functions_of_the_equation_language():
     from test_kernel_hostsim import elementwise_functions_model
     _fit_pair(pd.newPsydiff(**elementwise_functions_model()))
+
+
+def test_control_flow_in_the_statements():
+    from test_kernel_hostsim import control_flow_model
+    _fit_pair(pd.newPsydiff(**control_flow_model()))
