@@ -33,6 +33,10 @@ def case(name, config, kw, grad=True, first_rows=None):
         g = R.gradients()
         assert list(g) == out["labels"]
         out["getGradients"] = list(g.values())
+        # the same finite difference evaluated by the oracle's 80-bit build: how far the reference's own double-precision
+        # gradient is from the exact value of its formulation (the allowance the parity checks add to the 1e-6 gate)
+        from oracle.oracle import Oracle
+        out["grad_80bit"] = Oracle(m, extended=True).gradients(nthreads=8)["grad_clean"].tolist()
     json.dump(out, open(os.path.join(HERE, f"{name}_reference.json"), "w"), indent=1)
     print(name, "sum(-2LL) =", float(np.sum(fit["m2LL"])))
 
@@ -41,7 +45,7 @@ def main():
     case("c1", "C1: 2x2 OU, N=20, T=50, rk4 h=1/30, eps=1e-6 central, seed 20210129 (synth.config_c1())", synth.config_c1())
     case("c1_missing_cov", "C1 model, covariance variant (srUpdate=FALSE), N=24, T=30, 20 % missing, seed 9 "
          "(synth.config_c1(N=24, T=30, missing=0.2, seed=9, srUpdate=False))", synth.config_c1(N=24, T=30, missing=0.2, seed=9, srUpdate=False))
-    case("c3", "C3: Van der Pol, mu | person, dopri5, N=16, T=12 (synth.config_c3(N=16, T=12))", synth.config_c3(N=16, T=12), grad=False)
+    case("c3", "C3: Van der Pol, mu | person, dopri5, N=16, T=12, eps=1e-6 central (synth.config_c3(N=16, T=12))", synth.config_c3(N=16, T=12))
     case("c4", "C4: 3 coupled Van der Pol (n=m=6), irregular dt, 8 groups, N=16, T=12, rk4 h=min(dt)/30, eps=1e-6 central, seed 20210132 "
          "(synth.config_c4(N=16, T=12)); note: the reference's double-precision FD gradient of this model carries ~1e-4 relative "
          "rounding noise (see c4_oracle_ext.json for the 80-bit value)", synth.config_c4(N=16, T=12))

@@ -21,7 +21,7 @@ CASES = {
 
 def load(name):
     d = json.load(open(os.path.join(HERE, "golden", f"{name}_reference.json")))
-    for k in ("m2LL", "latentScores_first_person", "predictedManifest_first_person", "getGradients"):
+    for k in ("m2LL", "latentScores_first_person", "predictedManifest_first_person", "getGradients", "grad_80bit"):
         if k in d:
             d[k] = np.array(d[k], dtype=float)
     return d
@@ -41,10 +41,12 @@ def check_fit(fit, ref, rtol=1e-9):
 
 def check_gradient(g, ref, eps=1e-6, exact=None):
     """FD gradient against the reference's getGradients: 1e-6 relative plus the rounding floor of a double-precision finite
-    difference of Σ-2LL (both sides evaluate Σ-2LL to a few ulp and divide by 2 eps).  `exact` (the 80-bit oracle's gradient,
-    tests/golden/c4_oracle_ext.json) widens the allowance by the reference's OWN distance from it: on the nonlinear C4 model the
-    reference's double-precision gradient is ~1e-4 relative away from the exact finite difference."""
+    difference of Σ-2LL (both sides evaluate Σ-2LL to a few ulp and divide by 2 eps).  The fixture's `grad_80bit` (the same finite
+    difference by the oracle's 80-bit build) widens the allowance by the reference's OWN distance from the exact value of its
+    formulation: on the nonlinear C4 model and under adaptive stepping (C3) the reference's double-precision gradient is
+    ~1e-4 relative away from it."""
     gr = ref["getGradients"]
+    exact = ref.get("grad_80bit") if exact is None else exact
     atol = 64 * np.finfo(float).eps * abs(float(np.sum(ref["m2LL"]))) / (2 * eps)
     allow = 1e-6 * np.abs(gr) + atol
     if exact is not None:

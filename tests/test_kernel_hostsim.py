@@ -192,10 +192,7 @@ def test_kernel_source_equals_reference_run_fixtures(name):
     hs = HostSim(model)
     rf.check_fit(hs.fit(), ref)
     if "getGradients" in ref:
-        exact = None
-        if name == "c4":
-            exact = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c4_oracle_ext.json")))["grad_clean"]
-        rf.check_gradient(hs.gradients(eps=1e-6)["grad"], ref, exact=exact)
+        rf.check_gradient(hs.gradients(eps=1e-6)["grad"], ref)
 
 
 def operator_surface_model(**settings):

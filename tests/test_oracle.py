@@ -208,10 +208,7 @@ def test_oracle_equals_reference_run_fixtures(name):
         assert rel < 1e-12
     if "getGradients" in ref:
         g = o.gradients(nthreads=8)
-        exact = None
-        if name == "c4":
-            exact = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c4_oracle_ext.json")))["grad_clean"]
-        rf.check_gradient(g["grad_ref"], ref, exact=exact)
+        rf.check_gradient(g["grad_ref"], ref)
 
 
 def test_dormand_prince_tableau_equals_scipys_in_all_three_implementations():
