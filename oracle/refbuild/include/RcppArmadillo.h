@@ -10,7 +10,9 @@
 //                    stop / warning.                       Rcpp sugar `unique()` is hash ordered; here: first appearance.
 //   Armadillo      : dense double matrices, column-major; mat / colvec / rowvec / uvec; col / row / rows / cols / submat /
 //                    elem / diag / span views; each_col; trans, inv, inv(trimatl), trimatl, chol("lower"), qr_econ, det,
-//                    eye, diagmat, log, exp, sum, find, find_finite, find_nonfinite, is_finite, min.
+//                    eye, diagmat, log, exp, sum, find, find_finite, find_nonfinite, is_finite, min; and, for user equations,
+//                    % and element-wise /, dot, accu, mean, norm, max, as_scalar, sin / cos / tanh / sqrt / abs / square / pow,
+//                    expm (scaling and squaring around a degree-12 Taylor polynomial).
 //                    LAPACK-backed routines (inv, chol, qr_econ, det) are textbook algorithms here: unblocked Householder
 //                    QR, Cholesky, LU with partial pivoting, forward substitution for triangular inverses.
 // Not a general implementation of either library.
