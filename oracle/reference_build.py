@@ -139,6 +139,21 @@ def build(spec) -> str:
     return so
 
 
+def prune():
+    """Delete binaries in oracle/_ref that the manifest no longer points at (left behind when a header or a model changed)."""
+    import json
+    mf = os.path.join(_OUT, "manifest.json")
+    if not os.path.exists(mf):
+        return 0
+    keep = set(json.load(open(mf)).values())
+    n = 0
+    for f in os.listdir(_OUT):
+        if f.startswith("ref_") and f.endswith(".so") and f not in keep:
+            os.remove(os.path.join(_OUT, f))
+            n += 1
+    return n
+
+
 class _Container(C.Structure):
     _fields_ = [("name", C.c_char_p), ("is_scalar", C.c_int), ("rows", C.c_int), ("cols", C.c_int), ("values", C.POINTER(C.c_double))]
 
