@@ -324,7 +324,10 @@ def main():
         },
     }
     gvals = np.array(list(g.values()))
-    line["check"] = {"m2ll_total": total, "finite": bool(np.isfinite(total) and np.isfinite(gvals).all())}
+    # the timed result itself, so that a bench line can be re-derived elsewhere (tools/bench_total_crosscheck.py does it for
+    # m2ll_total with the kernel source compiled for the host)
+    line["check"] = {"m2ll_total": total, "finite": bool(np.isfinite(total) and np.isfinite(gvals).all()),
+                     "grad_l2": float(np.linalg.norm(gvals)), "grad_head": {k: float(g[k]) for k in list(g)[:4]}}
     if world == 1 and not args.no_cpu_baseline:
         val, cores, desc, sec = cpu_sample(args, model)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "seconds": sec}
