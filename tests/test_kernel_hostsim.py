@@ -357,3 +357,48 @@ def test_control_flow_in_the_statements():
 def codegen_dep(model):
     from psydiff_b200 import codegen
     return codegen.drift_dependency(model["_spec"])
+
+
+def test_eps_fallback_sweep_on_the_cpu_with_the_library_bookkeeping():
+    """eps = c(30, 1e-6) end to end without a GPU: instance results from the host-compiled kernel source, the partial-sum vector
+    [Σf0, #nonfinite, D+, D-, nf+, nf-, nbt] formed as the reduction kernels form it, the library's host bookkeeping
+    (psy_sweep_resolve / psy_sweep_finish) deciding which sides fall back to the second step — against the oracle's gradient."""
+    import ctypes as C
+    from psydiff_b200 import _lib
+    model = pd.newPsydiff(**synth.config_c1(N=10, T=50, eps=np.array([30.0, 1e-6]), A0=np.eye(2)))
+    hs = HostSim(model)
+    P = hs.P
+    L = _lib.lib()
+    sweep = L.psy_sweep_create(P)
+    need, done = np.zeros(2 * P + 1, dtype=np.uint8), C.c_int(0)
+    used_fallback = False
+    for level, eps in enumerate(model["eps"]):
+        inst, start, distinct = hs.instance_list(pad=True)
+        f = hs._launch(inst, len(inst), hs.theta(), float(eps))
+        part = np.zeros(5 * P + 2)
+        f0 = np.array([f[int(start[p])] for p in range(hs.N)])
+        part[0], part[1] = f0[np.isfinite(f0)].sum() if not np.isfinite(f0).all() else f0.sum(), (~np.isfinite(f0)).sum()
+        for p in range(hs.N):
+            o = int(start[p])
+            f0s = f0[p] if np.isfinite(f0[p]) else 0.0
+            for j, t in enumerate(distinct[p]):
+                fm, fp = f[o + 1 + 2 * j], f[o + 2 + 2 * j]
+                part[2 + t] += fp - f0s                          # D+
+                part[2 + P + t] += fm - f0s                      # D-
+                part[2 + 2 * P + t] += 0.0 if np.isfinite(fp) else 1.0
+                part[2 + 3 * P + t] += 0.0 if np.isfinite(fm) else 1.0
+                part[2 + 4 * P + t] += 0.0 if np.isfinite(f0[p]) else 1.0
+        if level > 0:
+            used_fallback = bool(need[:2 * P].any())
+        _lib.check(L.psy_sweep_resolve(sweep, _lib.dptr(part), float(eps), level, len(model["eps"]), 0, _lib.u8ptr(need), C.byref(done)))
+        if done.value:
+            break
+    g, tot = np.zeros(P), C.c_double()
+    _lib.check(L.psy_sweep_finish(sweep, 0, _lib.dptr(g), C.byref(tot)))
+    L.psy_sweep_destroy(sweep)
+    ref = _oracle(model).gradients()
+    assert used_fallback                                        # some sides did fail at eps = 30 and were redone at 1e-6
+    assert np.array_equal(np.isfinite(g), np.isfinite(ref["grad_clean"]))
+    fin = np.isfinite(g)
+    assert np.allclose(g[fin], ref["grad_clean"][fin], rtol=1e-6, atol=1e-6 * np.abs(ref["grad_clean"][fin]).max())
+    assert tot.value == pytest.approx(float(ref["m2LL"].sum()), rel=1e-12)
