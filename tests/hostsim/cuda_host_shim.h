@@ -42,4 +42,8 @@ static inline double psy_sim_rsqrt_seed(double x) {
   return r;
 }
 
+#ifdef PSY_COUNT_OPS
+#include "op_counter.h"     // from here on `double` is the counting wrapper (sizeof 8, same layout): the kernel source below counts its flops
+#endif
+
 namespace psy { double psy_smem[1 << 14]; }  // dynamic shared memory of the ONE simulated thread block (single host thread)

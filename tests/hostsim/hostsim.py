@@ -35,6 +35,12 @@ extern "C" void psy_hostsim_run(const PsyLaunch* L, int block) {
     }
 }
 extern "C" int psy_hostsim_block(void) { return PSY_BLOCK; }
+#ifdef PSY_COUNT_OPS
+extern "C" void psy_hostsim_ops(unsigned long long* out, int reset) {
+  out[0] = psy_ops::add; out[1] = psy_ops::mul; out[2] = psy_ops::fma_; out[3] = psy_ops::div_; out[4] = psy_ops::special;
+  if (reset) psy_ops::add = psy_ops::mul = psy_ops::fma_ = psy_ops::div_ = psy_ops::special = 0;
+}
+#endif
 extern "C" const int* psy_hostsim_info(void) { return psy_module_info; }
 """
 
@@ -160,6 +166,15 @@ class HostSim:
 
     def theta(self):
         return np.ascontiguousarray(self.model["pars"]["parameterTable"].theta_values, dtype=np.float64)
+
+    def ops(self, reset=True):
+        """Floating-point operations the kernel SOURCE executed since the last reset (only with extra_flags "-DPSY_COUNT_OPS"):
+        dict(add, mul, fma, div, special); flops = add + mul + 2 fma + div + special."""
+        out = (C.c_ulonglong * 5)()
+        self.lib.psy_hostsim_ops(out, 1 if reset else 0)
+        d = dict(zip(("add", "mul", "fma", "div", "special"), (int(v) for v in out)))
+        d["flops"] = d["add"] + d["mul"] + 2 * d["fma"] + d["div"] + d["special"]
+        return d
 
     def fit(self, theta=None, skip_update=False, states=True):
         """psy_fit: base instances only -> per-person -2LL (+ latentScores rows x n, predictedManifest rows x m)."""

@@ -402,3 +402,25 @@ def test_eps_fallback_sweep_on_the_cpu_with_the_library_bookkeeping():
     fin = np.isfinite(g)
     assert np.allclose(g[fin], ref["grad_clean"][fin], rtol=1e-6, atol=1e-6 * np.abs(ref["grad_clean"][fin]).max())
     assert tot.value == pytest.approx(float(ref["m2LL"].sum()), rel=1e-12)
+
+
+def test_flop_model_against_a_dynamic_count_of_the_kernel_source():
+    """psydiff_b200/flops.py's closed form (what bench.py's roofline starts from, before the ncu calibration) against the
+    operations the kernel SOURCE really executes: the host build with `double` replaced by a counting wrapper
+    (tests/hostsim/op_counter.h).  The dynamic count includes what the compiler later removes (drift components a sigma-point
+    column cannot move, time bookkeeping), so it sits a few per cent ABOVE the closed form; ncu's executed count sits 9 % below
+    it.  Same -2LL as the plain build, bit for bit."""
+    from psydiff_b200 import flops, codegen, _lib
+    L = _lib.lib()
+    model = pd.newPsydiff(**synth.config_c4(N=3, T=20))
+    hs = HostSim(model, "-DPSY_COUNT_OPS -std=c++20")
+    hs.ops()
+    f = hs.fit(states=False)["m2LL"]
+    ops = hs.ops()
+    assert np.array_equal(f, HostSim(model).fit(states=False)["m2LL"])
+    h = float(model["timeStep"][0])
+    steps = sum(L.psy_rk4_step_count(float(d), h) for d in model["data"]["dt"])
+    closed = flops.kernel_flops(6, 6, 39, 0, steps, len(model["data"]["dt"]), l_diag=True, dep=codegen.drift_dependency(model["_spec"]))
+    assert ops["div"] == 0                                  # no IEEE division anywhere on the path (reciprocals are seeded + Newton)
+    assert 1.0 <= ops["flops"] / closed <= 1.10, (ops, closed)
+    assert ops["fma"] * 2 > 0.45 * ops["flops"]             # about half of the flops are written as explicit FMAs
