@@ -409,7 +409,7 @@ def test_flop_model_against_a_dynamic_count_of_the_kernel_source():
     operations the kernel SOURCE really executes: the host build with `double` replaced by a counting wrapper
     (tests/hostsim/op_counter.h).  The dynamic count includes what the compiler later removes (drift components a sigma-point
     column cannot move, time bookkeeping), so it sits a few per cent ABOVE the closed form; ncu's executed count sits 9 % below
-    it.  Same -2LL as the plain build, bit for bit."""
+    it."""
     from psydiff_b200 import flops, codegen, _lib
     L = _lib.lib()
     model = pd.newPsydiff(**synth.config_c4(N=3, T=20))
@@ -417,7 +417,8 @@ def test_flop_model_against_a_dynamic_count_of_the_kernel_source():
     hs.ops()
     f = hs.fit(states=False)["m2LL"]
     ops = hs.ops()
-    assert np.array_equal(f, HostSim(model).fit(states=False)["m2LL"])
+    plain = HostSim(model).fit(states=False)["m2LL"]
+    assert np.max(np.abs(f - plain) / np.abs(plain)) < 1e-12          # same arithmetic (the wrapper only keeps a*b+c from contracting)
     h = float(model["timeStep"][0])
     steps = sum(L.psy_rk4_step_count(float(d), h) for d in model["data"]["dt"])
     closed = flops.kernel_flops(6, 6, 39, 0, steps, len(model["data"]["dt"]), l_diag=True, dep=codegen.drift_dependency(model["_spec"]))
