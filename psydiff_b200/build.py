@@ -13,7 +13,7 @@ FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-li
 def build_library(force: bool = False) -> str:
     out = os.path.join(_HERE, "libpsydiff_b200.so")
     srcs = [os.path.join(_HERE, "csrc", s) for s in SOURCES if os.path.exists(os.path.join(_HERE, "csrc", s))]
-    deps = srcs + [os.path.join(_HERE, "csrc", h) for h in ("psy_launch.h",)] + \
+    deps = srcs + [os.path.join(_HERE, "csrc", h) for h in ("psy_launch.h", "psy_reduce.cuh")] + \
         [os.path.join(_HERE, "..", "include", "psydiff_b200.h")]
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out

@@ -13,7 +13,15 @@
 #define __host__
 #define __global__
 #define __forceinline__ inline
+#ifdef PSY_SIM_BLOCK_THREADS
+// block-level kernels (K3): one host thread per CUDA thread of ONE block at a time; __shared__ arrays become statics that the
+// block's threads share, __syncthreads() a barrier over blockDim.x threads (psy_sim_barrier, set up by the launcher)
+#define __shared__ static
+void psy_sim_barrier();
+#define __syncthreads() psy_sim_barrier()
+#else
 #define __shared__
+#endif
 #define __restrict__
 #define __launch_bounds__(...)
 

@@ -425,3 +425,50 @@ def test_flop_model_against_a_dynamic_count_of_the_kernel_source():
     assert ops["div"] == 0                                  # no IEEE division anywhere on the path (reciprocals are seeded + Newton)
     assert 1.0 <= ops["flops"] / closed <= 1.10, (ops, closed)
     assert ops["fma"] * 2 > 0.45 * ops["flops"]             # about half of the flops are written as explicit FMAs
+
+
+def test_reduction_kernels_k3_on_the_cpu():
+    """psy_reduce.cuh (K3) compiled for the host — psy_reduce_chunks with real threads and a barrier for __syncthreads() — against
+    numpy: D± = Σ_p (f±_p − f0_p) with a non-finite f0 treated as 0, the non-finite counts per side, the base pseudo-segment,
+    multi-chunk parameters (> 4096 persons), small segments (person-specific parameters), and bit-reproducibility."""
+    from hostsim import k3sim
+    rng = np.random.default_rng(0)
+    N, F = 9000, 6
+    n_common, n_group = 3, 5                         # 3 parameters shared by everybody (3 chunks each), 5 group labels, N person-specific
+    P = n_common + n_group + N
+    tidx = np.empty((N, F), dtype=np.int32)
+    tidx[:, :3] = np.arange(n_common)
+    tidx[:, 3] = n_common + rng.integers(0, n_group, N)
+    tidx[:, 4] = tidx[:, 3]                          # a second slot carrying the same label: counted once per person
+    tidx[:, 5] = n_common + n_group + np.arange(N)
+    ls = k3sim.lists(tidx, P)
+    assert len(ls["small"]) == N and len(ls["big"]) == n_common + n_group + 1 and len(ls["chunks"]) == 3 * n_common + n_group + 3
+    f = rng.standard_normal(ls["n_inst"]) * 3 + 50
+    bad = rng.choice(ls["n_inst"], 40, replace=False)
+    f[bad[:20]] = np.nan
+    f[bad[20:30]] = np.inf
+    f[bad[30:]] = -np.inf
+    f[ls["start"][5]], f[ls["start"][4711]] = np.nan, np.inf       # two persons whose BASE instance failed
+    part = k3sim.reduce(f, ls, P)
+    assert np.array_equal(part, k3sim.reduce(f, ls, P), equal_nan=True)                 # deterministic, bit for bit
+    start, distinct = ls["start"], ls["distinct"]
+    f0 = f[start]
+    want = np.zeros(5 * P + 2)
+    want[0], want[1] = f0.sum(), (~np.isfinite(f0)).sum()
+    with np.errstate(invalid="ignore"):
+        for p in range(N):
+            f0s = f0[p] if np.isfinite(f0[p]) else 0.0
+            for j, t in enumerate(distinct[p]):
+                fm, fp = f[start[p] + 1 + 2 * j], f[start[p] + 2 + 2 * j]
+                want[2 + t] += fp - f0s
+                want[2 + P + t] += fm - f0s
+                want[2 + 2 * P + t] += 0.0 if np.isfinite(fp) else 1.0
+                want[2 + 3 * P + t] += 0.0 if np.isfinite(fm) else 1.0
+                want[2 + 4 * P + t] += 0.0 if np.isfinite(f0[p]) else 1.0
+    cnt = slice(2 + 2 * P, 2 + 5 * P)
+    assert np.array_equal(part[cnt], want[cnt]) and part[1] == want[1]                  # counts exactly
+    fin = np.isfinite(want)
+    assert np.array_equal(fin, np.isfinite(part))                                       # a non-finite f± makes that D± non-finite
+    assert np.allclose(part[fin], want[fin], rtol=1e-12, atol=1e-9)                     # sums to rounding (different tree)
+    assert not np.isfinite(part[0]) and part[1] >= 2                                    # Σ f0 carries the failed base instances, counted
+    assert part[2 + 4 * P + 0] == part[1]                                               # nbt of a common parameter = all failed persons
