@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--outer", type=int, default=15)
     ap.add_argument("--bfgs-iters", type=int, default=5)
     ap.add_argument("--batch", type=int, default=8, help="line-search candidates evaluated per launch")
+    ap.add_argument("--progress", default="", help="rank 0 appends one JSON line per gradient evaluation (= per GIST outer iteration) here")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -42,14 +43,40 @@ def main():
     pd.compileModel(model)
     start = pd.getParameterValues(model)
     gains = [k for k in start if k.startswith("k") and k[1:].isdigit()]
+    t_start = time.time()
+    calls = {"grad": 0, "fit": 0}
+
+    def progress(kind, seconds, **extra):
+        if rank == 0 and a.progress:
+            with open(a.progress, "a") as f:
+                f.write(json.dumps(dict(kind=kind, seconds=round(seconds, 3), since_start=round(time.time() - t_start, 3), **extra)) + "\n")
+
+    def gradients_logged(m, **kw):
+        t = time.time()
+        g = pdist.getGradientsSharded(m, **kw)
+        calls["grad"] += 1
+        cur = pd.getParameterValues(m)
+        progress("gradient", time.time() - t, call=calls["grad"], zeroed=[k for k in gains if cur[k] == 0.0])
+        return g
+
+    def fits_logged(m, cands, **kw):
+        t = time.time()
+        out = pdist.fitTotalsSharded(m, cands, **kw)
+        calls["fit"] += len(cands)
+        progress("line_search_batch", time.time() - t, candidates=len(cands), totals=[float(x) for x in np.asarray(out)])
+        return out
+
+    progress("setup", 0.0, persons=npg * world, gpus=world, parameters=len(start))
     t0 = time.time()
     res = optim.GIST(model, start, lambda_=a.lam * npg * world / 2048, adaptiveLassoWeights={k: 1.0 for k in start},
                      regularizedParameters=gains, maxIter_out=a.outer, sig=.4, silent=True,
-                     fitTotal=pdist.fitTotalSharded, gradients=pdist.getGradientsSharded,
-                     batch=a.batch, fitTotalsMany=pdist.fitTotalsSharded)
+                     fitTotal=pdist.fitTotalSharded, gradients=gradients_logged,
+                     batch=a.batch, fitTotalsMany=fits_logged)
     t_gist = time.time() - t0
     est = pd.getParameterValues(model)
     names = list(est)
+    progress("gist_done", t_gist, regM2LL=[float(x) for x in res["regM2LL"][np.isfinite(res["regM2LL"])]],
+             gains={k: est[k] for k in gains})
     t0 = time.time()
     out = optim.vmmin(np.array(list(est.values())), lambda p: pdist.psydiffFitInternalSharded(p, names, model),
                       lambda p: pdist.psydiffGradientsInternalSharded(p, names, model), maxit=a.bfgs_iters)
@@ -60,7 +87,10 @@ def main():
             "persons": npg * world, "gpus": world, "gist_outer_iterations": int(len(r) - 1), "gist_seconds": t_gist,
             "seconds_per_outer_iteration": t_gist / max(len(r) - 1, 1), "regM2LL_first": float(r[0]), "regM2LL_last": float(r[-1]),
             "zeroed_gains": [k for k in gains if est[k] == 0.0], "kept_gains": {k: round(est[k], 4) for k in gains if est[k] != 0.0},
-            "bfgs_iterations": a.bfgs_iters, "bfgs_seconds": t_bfgs, "m2LL_after_bfgs": out["value"]}))
+            "bfgs_iterations": a.bfgs_iters, "bfgs_seconds": t_bfgs, "m2LL_after_bfgs": out["value"],
+            "gradient_evaluations": calls["grad"], "line_search_fits": calls["fit"],
+            "gains_after_bfgs": {k: round(float(v), 4) for k, v in zip(names, out["par"]) if k in gains},
+            "generating_gains": "ring neighbours k12 k23 k34 k41 = 0.08, the other eight 0"}))
     if world > 1:
         dist.destroy_process_group()
 

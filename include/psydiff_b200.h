@@ -89,6 +89,22 @@ void psy_model_destroy(psy_model* mdl);
  * properties of the generated kernel. */
 int psy_model_load_module(psy_model* mdl, const char* cubin_path);
 
+/* ---- devices: getGradientsParallel / compileParallelGradients (R/prepareModel.R:572-616) inside the library ----------
+ * The reference's only parallel path starts nCores PSOCK workers and ships them the model on every call.  Here ONE handle and
+ * ONE host thread drive several GPUs: persons are independent units (R/modelTemplate.R:244), so psy_upload cuts the dataset into
+ * contiguous person blocks balanced by filter work (Σ_t 1 + dt_t/h), every device filters its block on its own stream, and the
+ * per-parameter partial sums (5P+2 doubles per device) are added on the first device after peer copies over NVLink, in
+ * device order (deterministic).  A handle starts on the device that is current at psy_model_create.
+ *   n_devices = 0: all visible devices; device_ids = NULL: the creating device plus the next n_devices-1 visible ones.
+ * May be called at any time: a resident dataset and slot map are re-distributed from the library's pinned host copy. */
+int psy_device_count(void);
+int psy_model_set_devices(psy_model* mdl, int n_devices, const int* device_ids);
+/* number of devices in use (<= the number asked for when there are fewer persons); ids into device_ids[0..cap) */
+int psy_model_devices(const psy_model* mdl, int* device_ids, int cap);
+/* one device's share: its id, first person and person count, filter instances of a full sweep, kernel ms of the last launch */
+int psy_shard_info(const psy_model* mdl, int shard, int* device, int* first_person, int* n_persons, int64_t* n_instances,
+                   double* last_kernel_ms);
+
 /* Settings that fitModel reads back from the model list on every call (R/modelTemplate.R:169-176):
  * alpha, beta, kappa, timeStep[], integrateFunction; sr = srUpdate of newPsydiff (R/prepareModel.R:403). */
 int psy_model_settings(psy_model* mdl, double alpha, double beta, double kappa, int stepper,
@@ -126,10 +142,10 @@ int psy_gradients(psy_model* mdl, const double* theta, const double* eps, int n_
 int psy_gradient(psy_model* mdl, const double* theta, int par, const double* eps, int n_eps, int direction,
                  double* grad);
 
-/* ---- multi-GPU building blocks (persons sharded over ranks; one all-reduce per eps level) -------------------
+/* ---- multi-PROCESS building blocks (one rank per GPU or per node; one all-reduce per eps level) ---------------------
  * psy_grad_level runs this rank's instances at one eps value and leaves the partial-sum vector
  *   [ Σf0, #nonfinite f0, D+[P], D-[P], nf+[P], nf-[P], nbt[P] ]           (length psy_partial_len = 5P + 2)
- * in device memory (D± = Σ_p (f±_p − f0_p), nf± = # non-finite f±, nbt = # touched persons with non-finite f0).
+ * in device memory — on the handle's first device, already summed over the handle's own devices — (D± = Σ_p (f±_p − f0_p), nf± = # non-finite f±, nbt = # touched persons with non-finite f0).
  * need_side (2P bytes, [par*2 + side], NULL = all) restricts the launch to the (parameter, side) pairs still
  * unresolved — the eps[] fallback of R/modelTemplate.R:885-898.  The caller all-reduces (sum) the vector across
  * ranks (NCCL on the device pointer) and feeds the HOST copy of the reduced vector to psy_grad_resolve. */
@@ -153,7 +169,8 @@ int psy_sweep_finish(psy_sweep* s, int direction, double* grad, double* m2ll_tot
 
 /* ---- instrumentation ------------------------------------------------------------------------------------ */
 /* device time (ms, CUDA events on the launch stream) of the last filter-kernel launch, its instance count and
- * the number of kernels this library has launched since the last psy_counters_reset */
+ * the number of kernels this library has launched since the last psy_counters_reset; with several devices the time is the
+ * slowest device's (they run concurrently) and the instance count the sum */
 double psy_last_kernel_ms(const psy_model* mdl);
 int64_t psy_last_kernel_instances(const psy_model* mdl);
 int64_t psy_launch_count(void);

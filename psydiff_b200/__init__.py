@@ -5,7 +5,7 @@ Host-side mirror of the reference's R API (same names) over the C ABI of ``libps
 from ._lib import PsydiffError  # noqa: F401
 from .model import (  # noqa: F401
     newPsydiff, compileModel, compileModelSource, uploadData, fitModel, fitTotals, getGradients, getGradient, getGradientsParallel,
-    compileParallelGradients, stopParallelGradients, getParameterValues, setParameterValues, clonePsydiffModel,
+    compileParallelGradients, stopParallelGradients, setDevices, usedDevices, deviceCount, shardInfo, getParameterValues, setParameterValues, clonePsydiffModel,
     sdeModelMatrix, sepNameFromValue, chol2LogChol, extractParameters, makeGroups, checkEquation, fromMxMatrix,
 )
 from .codegen import modelTemplate, prepareEquations  # noqa: F401,E402

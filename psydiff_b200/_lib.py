@@ -50,6 +50,10 @@ SIGNATURES = {
     "psy_model_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_char_p]),
     "psy_model_destroy": (None, [C.c_void_p]),
     "psy_model_load_module": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "psy_device_count": (C.c_int, []),
+    "psy_model_set_devices": (C.c_int, [C.c_void_p, C.c_int, c_int_p]),
+    "psy_model_devices": (C.c_int, [C.c_void_p, c_int_p, C.c_int]),
+    "psy_shard_info": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p, c_int_p, c_int64_p, c_double_p]),
     "psy_model_settings": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, c_double_p, C.c_int, C.c_int]),
     "psy_upload": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, c_double_p, c_double_p, c_int64_p, c_int_p]),
     "psy_set_slots": (C.c_int, [C.c_void_p, C.c_int, c_int_p]),

@@ -34,13 +34,22 @@
 #include "psy_lang.cuh"
 
 #ifndef PSY_BLOCK
-#define PSY_BLOCK 64
+#define PSY_BLOCK 0   // 0 = by model size: 64 threads, 32 for N >= 7 (Filter::BLOCK)
 #endif
 #ifndef PSY_MIN_BLOCKS
 #define PSY_MIN_BLOCKS 1
 #endif
 #ifndef PSY_RHS_SCALED
 #define PSY_RHS_SCALED 1
+#endif
+#ifndef PSY_RHS_FUSED
+#define PSY_RHS_FUSED 0   // only meaningful with PSY_RHS_SCALED: diffusion term folded into the triangular product (rhs_fused)
+#endif
+#ifndef PSY_RHS_STREAM
+#define PSY_RHS_STREAM 0  // small-live-set ordering of rhs_scaled (rhs_stream)
+#endif
+#ifndef PSY_CHAIN_COLUMNS
+#define PSY_CHAIN_COLUMNS 1
 #endif
 
 namespace psy {
@@ -70,7 +79,8 @@ __device__ __forceinline__ double rcp(double x) {
 #endif
 }
 
-// PREPARED EXPERIMENT (-DPSY_RSQRT_ROT, off by default; checked on the host through tests/hostsim, not yet timed on the device):
+// Rotations from 1/sqrt (PSY_RSQRT_ROT: 1 = on, 0 = off, default -1 = on for N <= 6; timed on B200, profiles/r02a_experiments.txt:
+// C4 618.5 -> 610.7 ms, n = 8 806.8 -> 827.1 ms because the update's stack grows by 576 B there).
 // 1/sqrt(x) from the hardware seed (rsqrt.approx.ftz.f64) + two Newton steps, branch-free like rcp().  The Givens rotations of
 // the measurement update and the cholupdate steps then need no IEEE sqrt (≈ 16 instructions with a slow-path branch each) and
 // no reciprocal of the root: r = r²·r⁻¹, c = a·r⁻¹, s = b·r⁻¹.  sqrt(negative) = NaN either way; a ZERO radicand gives NaN here
@@ -90,11 +100,22 @@ __device__ __forceinline__ double rsq(double x) {
   return y;
 }
 
+#ifndef PSY_RSQRT_ROT
+#define PSY_RSQRT_ROT (-1)
+#endif
+
 template <class Mdl>
 struct Filter {
   static constexpr int N = Mdl::N, M = Mdl::M, F = Mdl::NFREE;  // NFREE >= 1 (padded); NSLOT real slots
   static constexpr int TN = N * (N + 1) / 2, TM = M * (M + 1) / 2;
   static constexpr int QLEN = (Mdl::L_STRUCT == L_DIAG) ? N : TN;
+  // Threads per block.  N >= 7: the state no longer fits the register file (1.1 KB spill frame at n = 8), and what bounds the kernel is
+  // where the spills live: measured on B200 (profiles/r02a_experiments.txt, n = 8) 8 resident warps per SM thrash the L1 that is left
+  // beside the RK4 parking area (L1 hit rate of spill loads 50 %, spill stores written through to L2 at 3.7 TB/s: 807 ms), 4 warps
+  // with a 45 % shared-memory carveout keep the frame L1-resident (776 ms), and one-warp blocks schedule best (736 ms).
+  static constexpr bool RSQ_ROT = (PSY_RSQRT_ROT == 1) || (PSY_RSQRT_ROT == -1 && Mdl::N <= 6);
+  static constexpr int BLOCK = (PSY_BLOCK > 0) ? PSY_BLOCK : ((N >= 7) ? 32 : 64);
+  static constexpr int SMEM_CARVEOUT_PCT = (N >= 7) ? 45 : -1;   // preferred shared-memory carveout (percent of the maximum), -1 = driver's choice
 
   struct UT { double sqrtc, wm0, wm1, wc0, wc1, kap; };
 
@@ -356,12 +377,262 @@ struct Filter {
       }
   }
 
+  // Fused form of the same RHS (default; -DPSY_RHS_FUSED=0 selects rhs_scaled).  The diffusion term is symmetric, so half of it
+  // can ride along with the drift differences through the ONE triangular product the RHS needs anyway:
+  //   D'_j = kap A_jj d_j + ½ (Q Wᵀ)_j,   H = W·[D'_1..D'_n] = G̃·diag(kap A_jj) + ½ W Q Wᵀ,   M̃ = H + Hᵀ,
+  //   Phi(M̃)_ij = H_ij + H_ji (i > j),  Phi(M̃)_jj = H_jj.
+  // For diagonal Q, (Q Wᵀ)_j has entries q_k W_jk for k <= j only, so the separate W diag(q) Wᵀ product of rhs_scaled
+  // (n(n-1)/2 multiplies + n(n-1)(n+1)/6 FMAs: 50 FP64 instructions at n = 6, 112 at n = 8) disappears, and Phi is assembled with one
+  // add per entry instead of two FMAs.  QH holds ½Q (run() halves it once per instance).  Same numbers up to rounding.
+  template <bool SCALE>
+  static __device__ __forceinline__ void rhs_fused(const double (&p)[F], const double (&m)[N], const double (&A)[TN],
+                                                   double (&dm)[N], double (&dA)[TN], double (&rd)[N], const double (&QH)[QLEN],
+                                                   const UT& ut, int person, double t) {
+    double At[TN], W[TN];   // strictly-lower entries are used, the unit diagonal is implied
+#pragma unroll
+    for (int i = 0; i < N; i++) rd[i] = rcp(A[tri(i, i)]);
+#pragma unroll
+    for (int j = 0; j < N; j++)
+#pragma unroll
+      for (int i = j + 1; i < N; i++) At[tri(i, j)] = A[tri(i, j)] * rd[j];
+#pragma unroll
+    for (int j = 0; j < N; j++)
+#pragma unroll
+      for (int i = j + 1; i < N; i++) {
+        double acc = -At[tri(i, j)];
+#pragma unroll
+        for (int k = j + 1; k < i; k++) acc = fma(-At[tri(i, k)], W[tri(k, j)], acc);
+        W[tri(i, j)] = acc;
+      }
+    Vec<N> xc, f0;
+#pragma unroll
+    for (int i = 0; i < N; i++) { xc.v[i] = m[i]; f0.v[i] = 0.0; }
+    Mdl::latentEquation(xc, f0, p, person, t);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      int unmoved = 0;
+#pragma unroll
+      for (int j = 0; j < N; j++) unmoved += ((Mdl::dep(i) >> j) != 0u) ? 0 : 1;
+      dm[i] = (ut.wm0 + 2.0 * (double)unmoved * ut.wm1) * f0.v[i];
+    }
+    double H[N * N];
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      Vec<N> xp, xm, fp, fm;
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        if (i >= j) {
+          xp.v[i] = fma(ut.sqrtc, A[tri(i, j)], m[i]);
+          xm.v[i] = fma(-ut.sqrtc, A[tri(i, j)], m[i]);
+        } else {
+          xp.v[i] = m[i];
+          xm.v[i] = m[i];
+        }
+        fp.v[i] = 0.0;
+        fm.v[i] = 0.0;
+      }
+      Mdl::latentEquation(xp, fp, p, person, t);
+      Mdl::latentEquation(xm, fm, p, person, t);
+      const double kaj = ut.kap * A[tri(j, j)];
+      // D'_j; entry k is structurally zero when k > j (no diffusion part) and column j cannot move drift component k
+      double d[N];
+      if constexpr (Mdl::L_STRUCT == L_DIAG) {
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+          const bool moved = (Mdl::dep(k) >> j) != 0u;
+          if (moved) dm[k] = fma(ut.wm1, fp.v[k] + fm.v[k], dm[k]);
+          if (k < j) {
+            const double hq = QH[k] * W[tri(j, k)];
+            d[k] = moved ? fma(kaj, fp.v[k] - fm.v[k], hq) : hq;
+          } else if (k == j) {
+            d[k] = moved ? fma(kaj, fp.v[k] - fm.v[k], QH[k]) : QH[k];
+          } else {
+            d[k] = moved ? kaj * (fp.v[k] - fm.v[k]) : 0.0;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+          double acc = d[i];
+#pragma unroll
+          for (int k = 0; k < i; k++)
+            if (k <= j || (Mdl::dep(k) >> j) != 0u) acc = fma(W[tri(i, k)], d[k], acc);
+          H[i + j * N] = acc;
+        }
+      } else {
+        // general L: ½ (Q Wᵀ)_j is a full column, QH = ½ L Lᵀ packed lower
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+          const bool moved = (Mdl::dep(k) >> j) != 0u;
+          if (moved) dm[k] = fma(ut.wm1, fp.v[k] + fm.v[k], dm[k]);
+          double acc = (k >= j) ? QH[tri(k, j)] : QH[tri(j, k)];
+#pragma unroll
+          for (int l = 0; l < j; l++) acc = fma((k >= l) ? QH[tri(k, l)] : QH[tri(l, k)], W[tri(j, l)], acc);
+          d[k] = moved ? fma(kaj, fp.v[k] - fm.v[k], acc) : acc;
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+          double acc = d[i];
+#pragma unroll
+          for (int k = 0; k < i; k++) acc = fma(W[tri(i, k)], d[k], acc);
+          H[i + j * N] = acc;
+        }
+      }
+    }
+    // Phi(M̃) and dA = (Ã Phi(M̃)) D⁻¹
+    double Ph[TN];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+      for (int j = 0; j <= i; j++) Ph[tri(i, j)] = (i == j) ? H[i + i * N] : H[i + j * N] + H[j + i * N];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+      for (int j = 0; j <= i; j++) {
+        double acc = Ph[tri(i, j)];
+#pragma unroll
+        for (int k = j; k < i; k++) acc = fma(At[tri(i, k)], Ph[tri(k, j)], acc);
+        dA[tri(i, j)] = SCALE ? acc * rd[j] : acc;
+      }
+  }
+
+  // Small-live-set form of rhs_scaled (-DPSY_RHS_STREAM=1; default for N >= 7, where the working set of rhs_scaled does not
+  // fit the register file and its spill STORES — write-through to L2 — set the pace, profiles/r02a_*).  Same arithmetic up to
+  // rounding, ordered so that the big temporaries never exist:
+  //   * Phi(M̃) starts as the diffusion part W diag(q) Wᵀ (needs W only) BEFORE the columns are visited;
+  //   * every column's G̃_j = W d_j is folded into Phi at once (Phi_max(i,j),min(i,j) += kap A_jj G̃_ij): G (n² doubles) is never stored;
+  //   * dA = (Ã Phi) D⁻¹ is evaluated as A·(D⁻¹ Phi), accumulating row by row of Phi: Ã (n(n-1)/2 doubles) is dead once W exists.
+  template <bool SCALE>
+  static __device__ __forceinline__ void rhs_stream(const double (&p)[F], const double (&m)[N], const double (&A)[TN],
+                                                    double (&dm)[N], double (&dA)[TN], double (&rd)[N], const double (&Q)[QLEN],
+                                                    const UT& ut, int person, double t) {
+    static_assert(Mdl::L_STRUCT == L_DIAG, "rhs_stream is written for diagonal L");
+    double W[TN], Ph[TN];
+    {
+      double At[TN];
+#pragma unroll
+      for (int i = 0; i < N; i++) rd[i] = rcp(A[tri(i, i)]);
+#pragma unroll
+      for (int j = 0; j < N; j++)
+#pragma unroll
+        for (int i = j + 1; i < N; i++) At[tri(i, j)] = A[tri(i, j)] * rd[j];
+#pragma unroll
+      for (int j = 0; j < N; j++)
+#pragma unroll
+        for (int i = j + 1; i < N; i++) {
+          double acc = -At[tri(i, j)];
+#pragma unroll
+          for (int k = j + 1; k < i; k++) acc = fma(-At[tri(i, k)], W[tri(k, j)], acc);
+          W[tri(i, j)] = acc;
+        }
+    }
+    // Phi <- W diag(q) Wᵀ (lower, diagonal halved)
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+      for (int j = 0; j <= i; j++) {
+        double acc = (i == j) ? Q[j] : W[tri(i, j)] * Q[j];
+#pragma unroll
+        for (int k = 0; k < j; k++) acc = fma(W[tri(i, k)] * Q[k], W[tri(j, k)], acc);
+        Ph[tri(i, j)] = (i == j) ? 0.5 * acc : acc;
+      }
+    Vec<N> xc, f0;
+#pragma unroll
+    for (int i = 0; i < N; i++) { xc.v[i] = m[i]; f0.v[i] = 0.0; }
+    Mdl::latentEquation(xc, f0, p, person, t);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      int unmoved = 0;
+#pragma unroll
+      for (int j = 0; j < N; j++) unmoved += ((Mdl::dep(i) >> j) != 0u) ? 0 : 1;
+      dm[i] = (ut.wm0 + 2.0 * (double)unmoved * ut.wm1) * f0.v[i];
+    }
+    // PSY_CHAIN_COLUMNS: column j + 1's sigma points are made to depend on the last value column j produces (sq + 0·g: an
+    // IEEE-exact no-op that neither nvvm nor ptxas may fold, because g could be NaN — in which case the instance is failing
+    // anyway).  Without it ptxas hoists all 2n drift evaluations to the top of the unrolled body for ILP and every d_j stays live.
+    double sq = ut.sqrtc;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      Vec<N> xp, xm, fp, fm;
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        if (i >= j) {
+          xp.v[i] = fma(sq, A[tri(i, j)], m[i]);
+          xm.v[i] = fma(-sq, A[tri(i, j)], m[i]);
+        } else {
+          xp.v[i] = m[i];
+          xm.v[i] = m[i];
+        }
+        fp.v[i] = 0.0;
+        fm.v[i] = 0.0;
+      }
+      Mdl::latentEquation(xp, fp, p, person, t);
+      Mdl::latentEquation(xm, fm, p, person, t);
+      double d[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        if ((Mdl::dep(i) >> j) != 0u) {
+          d[i] = fp.v[i] - fm.v[i];
+          dm[i] = fma(ut.wm1, fp.v[i] + fm.v[i], dm[i]);
+        } else {
+          d[i] = 0.0;
+        }
+      }
+      const double kaj = ut.kap * A[tri(j, j)];
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        bool any = (Mdl::dep(i) >> j) != 0u;
+        double acc = d[i];
+#pragma unroll
+        for (int k = 0; k < i; k++)
+          if ((Mdl::dep(k) >> j) != 0u) { acc = fma(W[tri(i, k)], d[k], acc); any = true; }
+        if (any) {   // G̃_ij enters Phi(M̃) at (max, min); twice on the diagonal, whose half is what Phi keeps
+          if (i >= j) Ph[tri(i, j)] = fma(acc, kaj, Ph[tri(i, j)]);
+          else Ph[tri(j, i)] = fma(acc, kaj, Ph[tri(j, i)]);
+        }
+#if PSY_CHAIN_COLUMNS
+        if (i == N - 1 && j + 1 < N) sq = fma(acc, 0.0, sq);
+#endif
+      }
+    }
+    // dA = A (D⁻¹ Phi) [D⁻¹]: row k of Phi seeds row k of dA and, scaled by 1/A_kk, feeds the rows below it
+#pragma unroll
+    for (int i = 0; i < TN; i++) dA[i] = Ph[i];
+#pragma unroll
+    for (int k = 0; k < N - 1; k++)
+#pragma unroll
+      for (int j = 0; j <= k; j++) {
+        const double ps = Ph[tri(k, j)] * rd[k];
+#pragma unroll
+        for (int i = k + 1; i < N; i++) dA[tri(i, j)] = fma(A[tri(i, k)], ps, dA[tri(i, j)]);
+      }
+    if (SCALE) {
+#pragma unroll
+      for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) dA[tri(i, j)] *= rd[j];
+    }
+  }
+
+  // the column-scaled RHS in use: fused (Q holds ½ L Lᵀ) or plain scaled (Q holds L Lᵀ)
+  static constexpr double Q_SCALE = (PSY_RHS_SCALED && PSY_RHS_FUSED && PSY_RHS_STREAM != 1) ? 0.5 : 1.0;
+  template <bool SCALE>
+  static __device__ __forceinline__ void rhs_col(const double (&p)[F], const double (&m)[N], const double (&A)[TN], double (&dm)[N],
+                                                 double (&dA)[TN], double (&rd)[N], const double (&Q)[QLEN], const UT& ut, int person, double t) {
+#if PSY_RHS_STREAM == 1
+    rhs_stream<SCALE>(p, m, A, dm, dA, rd, Q, ut, person, t);
+#elif PSY_RHS_FUSED
+    rhs_fused<SCALE>(p, m, A, dm, dA, rd, Q, ut, person, t);
+#else
+    rhs_scaled<SCALE>(p, m, A, dm, dA, rd, Q, ut, person, t);
+#endif
+  }
+
   static __device__ __forceinline__ void rhs(const double (&p)[F], const double (&m)[N], const double (&A)[TN],
                                              double (&dm)[N], double (&dA)[TN], const double (&Q)[QLEN],
                                              const UT& ut, int person, double t) {
 #if PSY_RHS_SCALED
     double rd[N];
-    rhs_scaled<true>(p, m, A, dm, dA, rd, Q, ut, person, t);
+    rhs_col<true>(p, m, A, dm, dA, rd, Q, ut, person, t);
 #else
     rhs_plain(p, m, A, dm, dA, Q, ut, person, t);
 #endif
@@ -377,21 +648,21 @@ struct Filter {
 #define PSY_RK4_SMEM (-1)
 #endif
   static constexpr bool RK4_SMEM = (PSY_RK4_SMEM == 1) || (PSY_RK4_SMEM == -1 && N >= 7);
-  static constexpr int SMEM_BYTES = RK4_SMEM ? 2 * (N + TN) * PSY_BLOCK * 8 : 0;
+  static constexpr int SMEM_BYTES = RK4_SMEM ? 2 * (N + TN) * BLOCK * 8 : 0;
   static __device__ __forceinline__ void rk4(const double (&p)[F], double (&m)[N], double (&A)[TN],
                                              const double (&Q)[QLEN], const UT& ut, int person, double h, int K) {
     if constexpr (RK4_SMEM) {
       extern __shared__ double psy_smem[];
       // volatile: the values must really be re-read from shared memory, not forwarded through registers
-      volatile double* sx = psy_smem + threadIdx.x;                       // x_n : sx[e * PSY_BLOCK]
-      volatile double* sa = psy_smem + (N + TN) * PSY_BLOCK + threadIdx.x;  // sum : sa[e * PSY_BLOCK]
+      volatile double* sx = psy_smem + threadIdx.x;                       // x_n : sx[e * BLOCK]
+      volatile double* sa = psy_smem + (N + TN) * BLOCK + threadIdx.x;  // sum : sa[e * BLOCK]
 #pragma unroll 1
       for (int step = 0; step < K; step++) {
         const double t0 = (double)step * h;
 #pragma unroll
-        for (int i = 0; i < N; i++) { sx[i * PSY_BLOCK] = m[i]; sa[i * PSY_BLOCK] = m[i]; }
+        for (int i = 0; i < N; i++) { sx[i * BLOCK] = m[i]; sa[i * BLOCK] = m[i]; }
 #pragma unroll
-        for (int i = 0; i < TN; i++) { sx[(N + i) * PSY_BLOCK] = A[i]; sa[(N + i) * PSY_BLOCK] = A[i]; }
+        for (int i = 0; i < TN; i++) { sx[(N + i) * BLOCK] = A[i]; sa[(N + i) * BLOCK] = A[i]; }
 #pragma unroll 1
         for (int st = 0; st < 4; st++) {
           double km[N], kA[TN];
@@ -399,7 +670,7 @@ struct Filter {
           const double b = (st == 0 || st == 3) ? h * (1.0 / 6.0) : h * (1.0 / 3.0);
           double rdv[N];
 #if PSY_RHS_SCALED
-          rhs_scaled<false>(p, m, A, km, kA, rdv, Q, ut, person, tc);   // D⁻¹ is folded into the step coefficients below
+          rhs_col<false>(p, m, A, km, kA, rdv, Q, ut, person, tc);   // D⁻¹ is folded into the step coefficients below
 #else
           rhs(p, m, A, km, kA, Q, ut, person, tc);
 #pragma unroll
@@ -408,10 +679,10 @@ struct Filter {
           // phased access: all loads first (they pipeline), then the arithmetic, then all stores
           double ta[N + TN], tx[N + TN];
 #pragma unroll
-          for (int i = 0; i < N + TN; i++) ta[i] = sa[i * PSY_BLOCK];
+          for (int i = 0; i < N + TN; i++) ta[i] = sa[i * BLOCK];
           if (st < 3) {
 #pragma unroll
-            for (int i = 0; i < N + TN; i++) tx[i] = sx[i * PSY_BLOCK];
+            for (int i = 0; i < N + TN; i++) tx[i] = sx[i * BLOCK];
             const double a = (st == 2) ? h : 0.5 * h;
 #pragma unroll
             for (int i = 0; i < N; i++) { ta[i] = fma(b, km[i], ta[i]); m[i] = fma(a, km[i], tx[i]); }
@@ -425,7 +696,7 @@ struct Filter {
               }
             }
 #pragma unroll
-            for (int i = 0; i < N + TN; i++) sa[i * PSY_BLOCK] = ta[i];
+            for (int i = 0; i < N + TN; i++) sa[i * BLOCK] = ta[i];
           } else {
 #pragma unroll
             for (int i = 0; i < N; i++) m[i] = fma(b, km[i], ta[i]);
@@ -456,7 +727,7 @@ struct Filter {
 #if PSY_RHS_SCALED
           // column scaling D⁻¹ of dA folded into the step coefficients
           double rdv[N];
-          rhs_scaled<false>(p, mt, At, km, kA, rdv, Q, ut, person, tc);
+          rhs_col<false>(p, mt, At, km, kA, rdv, Q, ut, person, tc);
 #pragma unroll
           for (int i = 0; i < N; i++) { ma[i] += b * km[i]; mt[i] = m[i] + a * km[i]; }
 #pragma unroll
@@ -681,21 +952,22 @@ struct Filter {
       for (int k = 0; k < M; k++) {
         if (k < first) continue;
         const double a = S[tri(k, k)], b = tr[k];
-#ifdef PSY_RSQRT_ROT
-        const double r2 = a * a + b * b;
-        const bool nz = r2 != 0.0;
-        const double ri = nz ? rsq(r2) : 0.0;      // a = b = 0: identity rotation (r = 0, c = 1, s = 0)
-        const double r = r2 * ri, s = b * ri;
-        const double c = nz ? a * ri : 1.0;
-#else
-        const double r = sqrt(a * a + b * b);
-        double c = 1.0, s = 0.0;
-        if (r != 0.0) {
-          const double ri = rcp(r);
-          c = a * ri;
+        double r, c = 1.0, s = 0.0;
+        if constexpr (RSQ_ROT) {
+          const double r2 = a * a + b * b;
+          const bool nz = r2 != 0.0;
+          const double ri = nz ? rsq(r2) : 0.0;      // a = b = 0: identity rotation (r = 0, c = 1, s = 0)
+          r = r2 * ri;
           s = b * ri;
+          c = nz ? a * ri : 1.0;
+        } else {
+          r = sqrt(a * a + b * b);
+          if (r != 0.0) {
+            const double ri = rcp(r);
+            c = a * ri;
+            s = b * ri;
+          }
         }
-#endif
         S[tri(k, k)] = r;
 #pragma unroll
         for (int j = k + 1; j < M; j++) {
@@ -750,19 +1022,18 @@ struct Filter {
 #pragma unroll
       for (int k = 0; k < M; k++) {
         const double lkk = S[tri(k, k)];
-#ifdef PSY_RSQRT_ROT
         const double r2 = lkk * lkk + dir * x[k] * x[k];
-        const double ri = rsq(r2);
-        const double r = r2 * ri;
+        double r, ic;
+        if constexpr (RSQ_ROT) {
+          const double ri = rsq(r2);
+          r = r2 * ri;
+          ic = lkk * ri;
+        } else {
+          r = sqrt(r2);
+          ic = lkk * rcp(r);
+        }
         const double il = rcp(lkk);
         const double c = r * il, s = x[k] * il;
-        const double ic = lkk * ri;
-#else
-        const double r = sqrt(lkk * lkk + dir * x[k] * x[k]);
-        const double il = rcp(lkk);
-        const double c = r * il, s = x[k] * il;
-        const double ic = lkk * rcp(r);
-#endif
         S[tri(k, k)] = r;
 #pragma unroll
         for (int i = k + 1; i < M; i++) {
@@ -791,19 +1062,18 @@ struct Filter {
 #pragma unroll
       for (int k = 0; k < N; k++) {
         const double lkk = A[tri(k, k)];
-#ifdef PSY_RSQRT_ROT
         const double r2 = lkk * lkk - x[k] * x[k];
-        const double ri = rsq(r2);
-        const double r = r2 * ri;
+        double r, ic;
+        if constexpr (RSQ_ROT) {
+          const double ri = rsq(r2);
+          r = r2 * ri;
+          ic = lkk * ri;
+        } else {
+          r = sqrt(r2);
+          ic = lkk * rcp(r);
+        }
         const double il = rcp(lkk);
         const double c = r * il, s = x[k] * il;
-        const double ic = lkk * ri;
-#else
-        const double r = sqrt(lkk * lkk - x[k] * x[k]);
-        const double il = rcp(lkk);
-        const double c = r * il, s = x[k] * il;
-        const double ic = lkk * rcp(r);
-#endif
         A[tri(k, k)] = r;
 #pragma unroll
         for (int i = k + 1; i < N; i++) {
@@ -912,7 +1182,7 @@ struct Filter {
         for (int j = 0; j <= i; j++) A[tri(i, j)] = (i == j) ? exp(A0[i + j * N]) : A0[i + j * N];  // logChol2Chol_C
       if constexpr (Mdl::L_STRUCT == L_DIAG) {
 #pragma unroll
-        for (int k = 0; k < N; k++) { const double l = exp(Ll[k + k * N]); Q[k] = l * l; }
+        for (int k = 0; k < N; k++) { const double l = exp(Ll[k + k * N]); Q[k] = Q_SCALE * (l * l); }
       } else {
 #pragma unroll
         for (int i = 0; i < N; i++) Ll[i + i * N] = exp(Ll[i + i * N]);
@@ -923,7 +1193,7 @@ struct Filter {
             double acc = 0.0;
 #pragma unroll
             for (int k = 0; k < N; k++) acc += Ll[i + k * N] * Ll[j + k * N];
-            Q[tri(i, j)] = acc;
+            Q[tri(i, j)] = Q_SCALE * acc;
           }
       }
     }
@@ -1018,10 +1288,14 @@ struct Filter {
 
 }  // namespace psy
 
-// psy_module_info = {stepper, srUpdate, nlatent, nmanifest, free slots, dynamic shared memory bytes}: lets the host check a module against its settings
+// psy_module_info = {stepper, srUpdate, nlatent, nmanifest, free slots, dynamic shared memory bytes, preferred shared-memory carveout in
+// percent (-1 = the driver's choice), threads per block}: lets the host check a module against its settings and launch it as it was built
 #define PSY_INSTANTIATE(MODEL)                                                                                      \
-  extern "C" __device__ const int psy_module_info[6] = {MODEL::STEPPER, MODEL::SR ? 1 : 0, MODEL::N, MODEL::M, MODEL::NSLOT, \
-                                                        MODEL::STEPPER == 0 ? psy::Filter<MODEL>::SMEM_BYTES : 0};           \
-  extern "C" __global__ void __launch_bounds__(PSY_BLOCK, PSY_MIN_BLOCKS) psy_filter_kernel(const PsyLaunch L) {   \
+  extern "C" __device__ const int psy_module_info[8] = {MODEL::STEPPER, MODEL::SR ? 1 : 0, MODEL::N, MODEL::M, MODEL::NSLOT, \
+                                                        MODEL::STEPPER == 0 ? psy::Filter<MODEL>::SMEM_BYTES : 0,            \
+                                                        MODEL::STEPPER == 0 ? psy::Filter<MODEL>::SMEM_CARVEOUT_PCT : -1,    \
+                                                        psy::Filter<MODEL>::BLOCK};                                          \
+  static constexpr int psy_block_size = psy::Filter<MODEL>::BLOCK;                                                 \
+  extern "C" __global__ void __launch_bounds__(psy::Filter<MODEL>::BLOCK, PSY_MIN_BLOCKS) psy_filter_kernel(const PsyLaunch L) {   \
     psy::Filter<MODEL>::run(L);                                                                                     \
   }

@@ -273,7 +273,9 @@ class PsydiffModel(dict):
         new = PsydiffModel()
         for k, v in self.items():
             if k in ("_handle",):
-                new[k] = v  # device handle and resident dataset are shared by clones (they are immutable)
+                new[k] = v  # device handle and resident dataset are shared by clones (uploadData refuses to replace it)
+                if v is not None:
+                    v.shared = True
             elif k == "data":
                 new[k] = v  # the dataset is never mutated
             else:
@@ -325,11 +327,7 @@ def newPsydiff(dataset, latentEquations, manifestEquations, L, Rchol, A0, m0, gr
     containers, slot_rows, startValues = extractParameters(list(parameters.keys()), parameters)
 
     # persons: contiguous row blocks (the reference writes to min(rowInd)+timePoint, R/modelTemplate.R:361)
-    change = np.flatnonzero(persons[1:] != persons[:-1]) + 1
-    row_off = np.concatenate([[0], change, [len(persons)]]).astype(np.int64)
-    persons_unique = persons[row_off[:-1]]
-    if len(np.unique(persons_unique)) != len(persons_unique):
-        raise PsydiffError("rows of one person must be contiguous in the dataset")
+    row_off, persons_unique = _person_blocks(persons)
     theta_labels, theta_values, theta_index = makeGroups(grouping, groupingvariables, slot_rows, persons_unique)
     ptab = ParameterTable(slot_rows, persons_unique, theta_labels, theta_values, theta_index)
 
@@ -418,23 +416,92 @@ def compileModel(psydiffModel, extra_flags: str = ""):
     return psydiffModel
 
 
+def _person_blocks(persons):
+    """Contiguous row blocks of the persons of a dataset (the reference writes to min(rowInd)+timePoint, R/modelTemplate.R:361)."""
+    persons = np.asarray(persons).reshape(-1)
+    change = np.flatnonzero(persons[1:] != persons[:-1]) + 1
+    row_off = np.concatenate([[0], change, [len(persons)]]).astype(np.int64)
+    persons_unique = persons[row_off[:-1]]
+    if len(np.unique(persons_unique)) != len(persons_unique):
+        raise PsydiffError("rows of one person must be contiguous in the dataset")
+    return row_off, persons_unique
+
+
 def uploadData(psydiffModel):
     """Copy model$data (host, R layout: observations rows x m column-major, dt, person blocks) into HBM.  compileModel
-    calls this once; call it again after replacing model["data"] with a dataset of the same persons (e.g. a new
-    simulation) — the slot map and the compiled kernel are kept."""
+    calls this once; call it again after replacing model["data"] with a dataset of the SAME persons in the same order (e.g. a
+    new simulation, other series lengths) — the slot map and the compiled kernel are kept.  The person blocks are recomputed
+    from the new data; a dataset with other persons is refused (the slot map belongs to the persons of newPsydiff), and so is
+    an upload through a handle that clones of the model share (it would swap the dataset under the other model objects)."""
     h = psydiffModel.get("_handle")
     if h is None or not h.ptr:
         raise PsydiffError("model is not compiled: call compileModel(model) first")
     data = psydiffModel["data"]
+    row_off, persons_unique = _person_blocks(data["person"])
+    old = np.asarray(psydiffModel["_persons_unique"])
+    if len(persons_unique) != len(old) or np.any(np.asarray(persons_unique) != old):
+        raise PsydiffError("uploadData: the dataset holds other persons (or another person order) than the model was built for; "
+                           "build a new model with newPsydiff")
+    if getattr(h, "uploaded", False) and getattr(h, "shared", False):
+        raise PsydiffError("uploadData: this device handle is shared with clones of the model; compile the clone itself "
+                           "(compileModel) before giving it other data")
     obs_cm = data["observations"]
     if not (isinstance(obs_cm, np.ndarray) and obs_cm.dtype == np.float64 and obs_cm.flags.f_contiguous):
         obs_cm = np.asfortranarray(obs_cm, dtype=np.float64)
     dt = np.ascontiguousarray(data["dt"], dtype=np.float64)
-    row_off = np.ascontiguousarray(psydiffModel["_row_off"], dtype=np.int64)
-    pid = np.ascontiguousarray(np.asarray(psydiffModel["_persons_unique"], dtype=np.float64).astype(np.int32))
+    if obs_cm.shape[0] != len(dt) or obs_cm.shape[0] != row_off[-1]:
+        raise PsydiffError("person, observations and dt must have the same number of rows")
+    psydiffModel["_row_off"] = row_off
+    pid = np.ascontiguousarray(np.asarray(persons_unique, dtype=np.float64).astype(np.int32))
     _lib.check(_lib.lib().psy_upload(h.ptr, obs_cm.shape[0], len(pid), obs_cm.ctypes.data_as(_lib.c_double_p), _lib.dptr(dt),
-                                     _lib.i64ptr(row_off), _lib.iptr(pid)))
+                                     _lib.i64ptr(row_off.astype(np.int64)), _lib.iptr(pid)))
+    h.uploaded = True
     return psydiffModel
+
+
+def deviceCount() -> int:
+    """Number of visible CUDA devices (0 without a driver)."""
+    return int(_lib.lib().psy_device_count())
+
+
+def setDevices(psydiffModel, devices=None):
+    """Give the compiled model the GPUs it runs on: ``None`` = all visible, an int n = the current device plus the next n-1,
+    or a list of device ids.  Persons are cut into contiguous blocks balanced by filter work, one block per device; fitModel,
+    getGradients and the optimisers then use all of them from this one process (include/psydiff_b200.h: psy_model_set_devices).
+    Returns the device ids in use."""
+    h = psydiffModel.get("_handle")
+    if h is None or not h.ptr:
+        raise PsydiffError("model is not compiled: call compileModel(model) first")
+    L = _lib.lib()
+    if devices is None:
+        _lib.check(L.psy_model_set_devices(h.ptr, 0, None))
+    elif isinstance(devices, (int, np.integer)):
+        _lib.check(L.psy_model_set_devices(h.ptr, int(devices), None))
+    else:
+        ids = np.ascontiguousarray(list(devices), dtype=np.int32)
+        _lib.check(L.psy_model_set_devices(h.ptr, len(ids), _lib.iptr(ids)))
+    return usedDevices(psydiffModel)
+
+
+def usedDevices(psydiffModel):
+    h = psydiffModel.get("_handle")
+    if h is None or not h.ptr:
+        return []
+    ids = np.zeros(64, dtype=np.int32)
+    n = int(_lib.lib().psy_model_devices(h.ptr, _lib.iptr(ids), 64))
+    return [int(x) for x in ids[:n]]
+
+
+def shardInfo(psydiffModel):
+    """Per device: id, first person, person count, filter instances of a full gradient sweep, kernel ms of the last launch."""
+    h = psydiffModel["_handle"]
+    out = []
+    for k in range(len(usedDevices(psydiffModel))):
+        dev, p0, n = C.c_int(), C.c_int(), C.c_int()
+        ni, ms = C.c_int64(), C.c_double()
+        _lib.check(_lib.lib().psy_shard_info(h.ptr, k, C.byref(dev), C.byref(p0), C.byref(n), C.byref(ni), C.byref(ms)))
+        out.append({"device": dev.value, "first_person": p0.value, "persons": n.value, "instances": ni.value, "last_kernel_ms": ms.value})
+    return out
 
 
 def _push_settings(model):
@@ -568,17 +635,22 @@ def getGradient(psydiffModel, currentParameterValues, par: int) -> Dict[str, flo
 
 
 def compileParallelGradients(psydiffModel, nCores: int = 1):
-    """compileParallelGradients (R/prepareModel.R:572-589).  The reference starts nCores PSOCK workers that each
-    recompile the model; here the parameter sweep is already one batched GPU launch, so this only compiles the
-    model (if needed) and sets ``model["cl"]`` so callers that test it (R/optimWrapper.R:169-177) take the same route."""
+    """compileParallelGradients (R/prepareModel.R:572-589).  The reference starts nCores PSOCK workers that each recompile the
+    model and receive it again on every call.  Here the workers are GPUs inside the library: the model is compiled (if needed)
+    and spread over min(nCores, visible devices) devices — one host thread, persons sharded, partial sums added over NVLink
+    (psy_model_set_devices).  ``model["cl"]`` is set so callers that test it (R/optimWrapper.R:169-177) take the same route."""
     if psydiffModel.get("_handle") is None:
         compileModel(psydiffModel)
-    psydiffModel["cl"] = {"nCores": int(nCores), "backend": "cuda-batched"}
+    n = max(1, min(int(nCores), deviceCount()))
+    used = setDevices(psydiffModel, n)
+    psydiffModel["cl"] = {"nCores": int(nCores), "backend": "cuda-batched", "devices": used}
     return psydiffModel
 
 
 def stopParallelGradients(psydiffModel):
-    """stopParallelGradients (R/prepareModel.R:598-600)."""
+    """stopParallelGradients (R/prepareModel.R:598-600): back to the one device the model was compiled on."""
+    if psydiffModel.get("cl") is not None and psydiffModel.get("_handle") is not None and len(usedDevices(psydiffModel)) > 1:
+        setDevices(psydiffModel, 1)
     psydiffModel["cl"] = None
 
 

@@ -29,7 +29,7 @@ def psydiffFitInternal(pars, parsnames=None, model=None) -> float:
     names, vals = _named(pars, parsnames)
     setParameterValues(model["pars"]["parameterTable"], vals, names)
     try:
-        fit = fitModel(model)
+        fit = fitModel(model, states=False)   # the optimiser only sums -2LL: no rows x (n + m) state matrices per evaluation
     except PsydiffError:
         return .5 * DOUBLE_XMAX
     if np.isnan(fit["m2LL"]).any():
@@ -229,7 +229,7 @@ def getStandardErrors(model, ndeps: float = 1e-3) -> Dict[str, float]:
 def fitf(pars: Dict[str, float], model) -> float:
     """fitf (R/GIST.R:285-289): Σ -2LL at the named parameter vector."""
     setParameterValues(model["pars"]["parameterTable"], pars)
-    return float(np.sum(fitModel(model)["m2LL"]))
+    return float(np.sum(fitModel(model, states=False)["m2LL"]))
 
 
 # ---------------------------------------------------------------------------------------------------------- GIST
@@ -275,7 +275,7 @@ def GIST(model, startingValues: Dict[str, float], lambda_, adaptiveLassoWeights:
             if fitTotal is not None:
                 tot = fitTotal(model)
                 return None if np.isnan(tot) else float(tot)
-            out = fitModel(model)
+            out = fitModel(model, states=False)
         except PsydiffError:
             return None
         return None if np.isnan(out["m2LL"]).any() else float(np.sum(out["m2LL"]))

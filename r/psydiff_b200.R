@@ -31,11 +31,35 @@ psydiffCudaSource <- function(nlatent, nmanifest, latentEquations, manifestEquat
   if (is.na(k)) stop("Unknown direction argument. Possible are central, left and right")
   k - 1L
 }
-.psy_settings <- function(m) list(c(m$alpha, m$beta, m$kappa), .psy_stepper(m$integrateFunction), as.numeric(m$timeStep),
-                                  isTRUE(m$srUpdate) || is.null(m$srUpdate))
+# srUpdate is a compile-time property of the kernel.  The reference bakes it into model$cppCode and keeps no field for it
+# (R/prepareModel.R:518-540); the patched newPsydiff therefore stores `srUpdate` and `cudaSpec` (the arguments of
+# psydiffCudaSource) in the model list, so that the variant can be read back and the source regenerated.
+.psy_sr <- function(m) if (is.null(m$srUpdate)) TRUE else isTRUE(m$srUpdate)
+.psy_settings <- function(m) list(c(m$alpha, m$beta, m$kappa), .psy_stepper(m$integrateFunction), as.numeric(m$timeStep), .psy_sr(m))
+.psy_variant <- function(m) c(if (identical(m$integrateFunction, "runge_kutta_dopri5")) 1L else 0L, as.integer(.psy_sr(m)))
+
+# state of the compiled model: the device handle, what its module was generated for, where the kernel headers and cache are
+.psy_env <- new.env(parent = emptyenv())
+
+# The reference reads model$integrateFunction on every fitModel call (R/modelTemplate.R:174); here the stepper and the update
+# variant are baked into the kernel, so a model whose (stepper, srUpdate) differ from the loaded module gets the matching
+# module (regenerated from model$cudaSpec, compiled once, cached by content hash) before it runs.
+.psy_variant_sync <- function(m) {
+  v <- .psy_variant(m)
+  if (!identical(v, .psy_env$variant)) {
+    sp <- m$cudaSpec
+    if (is.null(sp)) stop("model$cudaSpec is missing: build the model with the patched newPsydiff to change integrateFunction / srUpdate after compileModel")
+    src <- psydiffCudaSource(m$nlatent, m$nmanifest, sp$latentEquations, sp$manifestEquations, sp$parameterList,
+                             sp$parameterTableInit, .psy_sr(m), m$integrateFunction)
+    .Call("R_psy_load_module", .psy_env$handle, src, .psy_env$include, .psy_env$cache)
+    .psy_env$variant <- v
+  }
+  invisible(NULL)
+}
 
 # Make the handle hold THIS model's dataset and slot map (re-upload only when it is handed different R objects).
 .psy_sync <- function(handle, m) {
+  .psy_variant_sync(m)
   pt <- m$pars$parameterTable
   if (!.Call("R_psy_is_current", handle, m$data$observations, m$data$dt, m$data$person, pt$label)) {
     persons <- unique(m$data$person)
@@ -54,8 +78,12 @@ psydiffCudaSource <- function(nlatent, nmanifest, latentEquations, manifestEquat
 # any model object of the same structure, as the reference's do.
 compileModel <- function(psydiffModel) {
   nfree <- nrow(psydiffModel$pars$parameterTable) / length(unique(psydiffModel$data$person))
-  handle <- .Call("R_psy_compile", psydiffModel$cppCode, system.file("include", package = "psydiff"),
-                  tools::R_user_dir("psydiff", "cache"), psydiffModel$nlatent, psydiffModel$nmanifest, nfree)
+  .psy_env$include <- system.file("include", package = "psydiff")
+  .psy_env$cache <- tools::R_user_dir("psydiff", "cache")       # created recursively by psy_model_compile
+  handle <- .Call("R_psy_compile", psydiffModel$cppCode, .psy_env$include, .psy_env$cache, psydiffModel$nlatent,
+                  psydiffModel$nmanifest, nfree)
+  .psy_env$handle <- handle
+  .psy_env$variant <- .psy_variant(psydiffModel)                # model$cppCode was generated for these by newPsydiff
   assign("fitModel", function(psydiffModel, skipUpdate = FALSE) {
     .psy_sync(handle, psydiffModel)
     s <- .psy_settings(psydiffModel)
@@ -78,7 +106,19 @@ compileModel <- function(psydiffModel) {
   invisible(NULL)
 }
 
-# the PSOCK cluster of the reference is not needed: the whole parameter sweep is one batched launch
-compileParallelGradients <- function(psydiffModel, nCores) { psydiffModel$cl <- list(nCores = nCores); psydiffModel }
-stopParallelGradients <- function(psydiffModel) invisible(NULL)
+# compileParallelGradients (R/prepareModel.R:572-589): the reference starts nCores PSOCK workers, each recompiling the model,
+# and ships them the whole model on every getGradientsParallel call.  Here the workers are the GPUs of the box, inside the
+# library: the compiled model's persons are spread over min(nCores, visible devices) devices (one host thread, partial sums
+# added over NVLink).  fitModel / getGradients / getGradient use them from then on; getGradientsParallel is getGradients.
+compileParallelGradients <- function(psydiffModel, nCores) {
+  if (is.null(.psy_env$handle)) compileModel(psydiffModel)
+  .psy_sync(.psy_env$handle, psydiffModel)
+  devices <- .Call("R_psy_set_devices", .psy_env$handle, as.integer(nCores))
+  psydiffModel$cl <- list(nCores = nCores, devices = devices)
+  psydiffModel
+}
+stopParallelGradients <- function(psydiffModel) {
+  if (!is.null(.psy_env$handle)) .Call("R_psy_set_devices", .psy_env$handle, 1L)
+  invisible(NULL)
+}
 getGradientsParallel <- function(psydiffModel) getGradients(psydiffModel)

@@ -120,6 +120,25 @@ SEXP R_psy_load_module(SEXP h, SEXP cuda_src, SEXP incdir, SEXP cachedir) {
   return R_NilValue;
 }
 
+/* compileParallelGradients(psydiffModel, nCores) (R/prepareModel.R:572-589): the "workers" are GPUs inside the library — the
+ * handle's dataset is spread over min(nCores, visible devices) devices, one host thread (psy_model_set_devices).  Returns the
+ * device ids in use. */
+SEXP R_psy_set_devices(SEXP h, SEXP n_cores) {
+  psy_model* mdl = model_of(h);
+  int want = Rf_asInteger(n_cores);
+  const int visible = psy_device_count();
+  if (visible < 1) Rf_error("%s", psy_last_error());
+  if (want < 1) want = 1;
+  if (want > visible) want = visible;
+  CHECK(psy_model_set_devices(mdl, want, NULL));
+  int ids[64];
+  const int n = psy_model_devices(mdl, ids, 64);
+  SEXP out = PROTECT(Rf_allocVector(INTSXP, n));
+  for (int i = 0; i < n; i++) INTEGER(out)[i] = ids[i];
+  UNPROTECT(1);
+  return out;
+}
+
 static void push_settings(psy_model* mdl, SEXP settings, SEXP stepper, SEXP timeStep, SEXP sr) {
   CHECK(psy_model_settings(mdl, REAL(settings)[0], REAL(settings)[1], REAL(settings)[2], Rf_asInteger(stepper),
                            REAL(timeStep), LENGTH(timeStep), Rf_asLogical(sr)));
@@ -430,6 +449,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"R_psy_is_current", (DL_FUNC)&R_psy_is_current, 5},
     {"R_psy_upload", (DL_FUNC)&R_psy_upload, 9},
     {"R_psy_load_module", (DL_FUNC)&R_psy_load_module, 4},
+    {"R_psy_set_devices", (DL_FUNC)&R_psy_set_devices, 2},
     {"R_psy_fit", (DL_FUNC)&R_psy_fit, 8},
     {"R_psy_gradients", (DL_FUNC)&R_psy_gradients, 8},
     {"R_psy_gradient", (DL_FUNC)&R_psy_gradient, 9},

@@ -34,7 +34,7 @@ extern "C" void psy_hostsim_run(const PsyLaunch* L, int block) {
       psy_filter_kernel(*L);
     }
 }
-extern "C" int psy_hostsim_block(void) { return PSY_BLOCK; }
+extern "C" int psy_hostsim_block(void) { return psy_block_size; }
 #ifdef PSY_COUNT_OPS
 extern "C" void psy_hostsim_ops(unsigned long long* out, int reset) {
   out[0] = psy_ops::add; out[1] = psy_ops::mul; out[2] = psy_ops::fma_; out[3] = psy_ops::div_; out[4] = psy_ops::special;

@@ -17,6 +17,8 @@ struct psy_model {
   double checksum;  /* Σ of the finite observations, so that results depend on WHICH dataset is resident */
   double alpha;
   int stepper, sr;
+  int n_dev;        /* devices in use (psy_model_set_devices) */
+  int module_loads; /* psy_model_load_module calls */
 };
 
 static char g_err[512];
@@ -35,12 +37,26 @@ int psy_model_compile(const char* src, const char* inc, const char* cache, const
 psy_model* psy_model_create(int n, int m, int nfree, const char* cubin) {
   if (!cubin || strcmp(cubin, "mock.cubin") != 0) { fail(PSY_ERR_ARG, "bad cubin"); return NULL; }
   psy_model* M = (psy_model*)calloc(1, sizeof *M);
-  M->n = n; M->m = m; M->F = nfree;
+  M->n = n; M->m = m; M->F = nfree; M->n_dev = 1;
   g_live++;
   return M;
 }
 void psy_model_destroy(psy_model* M) { if (M) { g_live--; free(M); } }
-int psy_model_load_module(psy_model* M, const char* cubin) { (void)M; (void)cubin; return PSY_OK; }
+int psy_model_load_module(psy_model* M, const char* cubin) { (void)cubin; if (M) M->module_loads++; return PSY_OK; }
+int psy_mock_module_loads(const psy_model* M) { return M->module_loads; }
+/* a box with 4 devices */
+int psy_device_count(void) { return 4; }
+int psy_model_set_devices(psy_model* M, int n, const int* ids) {
+  (void)ids;
+  if (!M || n < 0) return fail(PSY_ERR_ARG, "psy_model_set_devices: bad arguments");
+  if (n > 4) return fail(PSY_ERR_ARG, "psy_model_set_devices: more devices asked for than visible");
+  M->n_dev = n == 0 ? 4 : n;
+  return PSY_OK;
+}
+int psy_model_devices(const psy_model* M, int* ids, int cap) {
+  for (int k = 0; k < M->n_dev && k < cap; k++) ids[k] = k;
+  return M->n_dev;
+}
 int psy_model_settings(psy_model* M, double alpha, double beta, double kappa, int stepper, const double* ts, int nts, int sr) {
   (void)beta; (void)kappa;
   if (!M || !ts || nts < 1) return fail(PSY_ERR_ARG, "psy_model_settings: bad arguments");

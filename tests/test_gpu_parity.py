@@ -3,6 +3,8 @@
 Gates (BASELINE.json north_star): per-person -2LL within 1e-9 relative; finite-difference gradients within 1e-6
 relative at eps = 1e-6 (entries with |g| < 1e-6 max|g| compared absolutely); identical non-finite pattern.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -21,7 +23,8 @@ def _oracle(model, extended=False):
 
 
 def _check_fit(model, states=True, skipUpdate=False):
-    pd.compileModel(model)
+    if model.get("_handle") is None:
+        pd.compileModel(model)
     fit = pd.fitModel(model, skipUpdate=skipUpdate)
     ref = _oracle(model).fit(skip_update=skipUpdate)
     fin = np.isfinite(ref["m2LL"])
@@ -40,14 +43,14 @@ def _check_fit(model, states=True, skipUpdate=False):
     return fit, ref
 
 
-def _check_grad(model, direction="central", extended=False):
+def _check_grad(model, direction="central", extended=False, nthreads=8):
     """extended=True compares with the 80-bit build of the oracle: the same reference algorithm with its own rounding
     noise removed.  Needed for nonlinear models, where the double build's FD noise exceeds the 1e-6 gate."""
     model["direction"] = direction
     if model.get("_handle") is None:
         pd.compileModel(model)
     g = pd.getGradients(model)
-    ref = _oracle(model, extended).gradients(direction=direction, nthreads=8)
+    ref = _oracle(model, extended).gradients(direction=direction, nthreads=nthreads)
     labels = model["pars"]["parameterTable"].theta_labels
     assert list(g.keys()) == labels
     gv, gr = np.array(list(g.values())), ref["grad_clean"]
@@ -221,10 +224,15 @@ def test_full_size_c2_properties():
     f = pd.fitModel(model)["m2LL"]
     assert np.isfinite(f).all() and f[0] == f[N - 1]          # identical persons -> bit-identical -2LL
     g = pd.getGradients(model)
-    # oracle on a 64-person subsample of the same model
-    sub = np.arange(0, N, N // 64)[:64]
-    ref = _oracle(model).fit(persons=sub, states=False)["m2LL"]
+    # oracle on a fixed 4096-person subsample of the same model, all host threads
+    sub = np.arange(0, N, N // 4096)[:4096]
+    ref = _oracle(model).fit(persons=sub, states=False, nthreads=os.cpu_count() or 1)["m2LL"]
     assert np.max(np.abs(f[sub] - ref) / np.abs(ref)) < M2LL_RTOL
+    # ... and the gradient of that subsample as its own model (Σ over 4096 persons of every parameter's central difference)
+    ks = dict(kw)
+    rows = (sub[:, None] * T + np.arange(T)[None, :]).reshape(-1)
+    ks["dataset"] = {k: v[rows] for k, v in kw["dataset"].items()}
+    _check_grad(pd.newPsydiff(**ks), nthreads=os.cpu_count() or 1)
     # linearity over person shards: Σ-2LL and the gradient of the halves add up to the whole
     halves = []
     for lo, hi in ((0, N // 2), (N // 2, N)):
@@ -334,3 +342,73 @@ def test_reference_run_fixtures(name):
     rf.check_fit(pd.fitModel(model), ref, rtol=M2LL_RTOL)
     if "getGradients" in ref:
         rf.check_gradient(np.array(list(pd.getGradients(model).values())), ref)
+
+
+@pytest.mark.parametrize("name", ["c3", "c4", "c5"])
+def test_subsample_4096_persons_at_benchmark_series_length(name):
+    """SURVEY §8(d)'s gate for the configs bench.py times: the CUDA path on a shard of the benchmark workload (T = 100, the
+    benchmark's stepper, time step and grouping) against the oracle on a fixed 4096-person subsample with all host threads
+    (-2LL within 1e-9 per person, identical non-finite pattern), and the FD gradient of a sub-model of its first persons against the 80-bit
+    oracle (1e-6 + FD noise floor; the double oracle's own distance is what DESIGN.md §5 explains).  C2 is covered at its full size
+    by test_full_size_c2_properties."""
+    nth = os.cpu_count() or 1
+    N, T = {"c3": 32768, "c4": 8192, "c5": 4096}[name], 100
+    kw = {"c3": synth.config_c3, "c4": synth.config_c4, "c5": synth.config_c5}[name](N=N, T=T)
+    model = pd.newPsydiff(**kw)
+    pd.compileModel(model)
+    f = pd.fitModel(model, states=False)["m2LL"]
+    sub = np.arange(0, N, N // 4096)[:4096]
+    ref = _oracle(model).fit(persons=sub, states=False, nthreads=nth)["m2LL"]
+    assert np.array_equal(np.isfinite(ref), np.isfinite(f[sub]))
+    fin = np.isfinite(ref)
+    rel = np.abs(f[sub][fin] - ref[fin]) / np.abs(ref[fin])
+    print(f"{name}: 4096-person subsample of {N} x T={T}: max rel -2LL error vs oracle {rel.max():.3e}, non-finite persons {int((~fin).sum())}")
+    assert rel.max() < M2LL_RTOL and fin.mean() > 0.99
+    n_g = {"c3": 256, "c4": 48, "c5": 16}[name]          # the 80-bit oracle runs 2P+1 sweeps per person: sized for about 20 s on 16 threads
+    rows = (sub[:n_g, None] * T + np.arange(T)[None, :]).reshape(-1)
+    ks = dict(kw)
+    ks["dataset"] = {k: v[rows] for k, v in kw["dataset"].items()}
+    _check_grad(pd.newPsydiff(**ks), extended=True, nthreads=nth)
+
+
+def test_several_devices_in_one_handle_equal_one_device():
+    """psy_model_set_devices: persons cut into work-balanced blocks over the GPUs of the box, one host thread.  Per-person results
+    (-2LL, latent scores, predictions) are independent of the cut — bit-identical; parameter sums differ by summation order only
+    (<= 1e-12); the eps[] fallback and one-sided sweeps run on every device; going back to one device reproduces the first result
+    bit for bit.  Needs >= 2 GPUs (gpurun --gpus 2)."""
+    if pd.deviceCount() < 2:
+        pytest.skip("needs at least two GPUs")
+    nd = min(pd.deviceCount(), 8)
+    # ragged persons with person-specific parameters: the cuts are placed by work, not by count
+    kw = synth.config_c3(N=1500, T=30, integrateFunction="rk4")
+    keep = np.ones(1500 * 30, dtype=bool)
+    for p in range(0, 700, 2):
+        keep[p * 30 + 8:(p + 1) * 30] = False                 # the first persons have short series
+    kw["dataset"] = {k: v[keep] for k, v in kw["dataset"].items()}
+    for direction, eps in (("central", np.array([1e-6])), ("left", np.array([1e-6])), ("central", np.array([30.0, 1e-6]))):
+        model = pd.newPsydiff(**dict(kw, direction=direction, eps=eps))
+        pd.compileModel(model)
+        one = pd.fitModel(model)
+        g1 = np.array(list(pd.getGradients(model).values()))
+        t1, b1 = pd.fitTotals(model, [pd.getParameterValues(model)] * 2)
+        used = pd.setDevices(model, nd)
+        assert used == list(range(nd)) or len(used) == nd
+        info = pd.shardInfo(model)
+        assert sum(s["persons"] for s in info) == 1500 and info[0]["persons"] > info[-1]["persons"]     # short series first: more persons there
+        many = pd.fitModel(model)
+        for k in ("m2LL", "latentScores", "predictedManifest"):
+            assert np.array_equal(one[k], many[k], equal_nan=True), k
+        gn = np.array(list(pd.getGradients(model).values()))
+        assert np.array_equal(np.isfinite(g1), np.isfinite(gn))
+        fin = np.isfinite(g1)
+        assert np.max(np.abs(gn[fin] - g1[fin]) / np.maximum(np.abs(g1[fin]), 1e-12)) < 1e-12
+        tn, bn = pd.fitTotals(model, [pd.getParameterValues(model)] * 2)
+        assert np.allclose(tn, t1, rtol=1e-13) and np.array_equal(bn, b1)
+        assert pd.setDevices(model, 1) == used[:1]
+        assert np.array_equal(np.array(list(pd.getGradients(model).values())), g1, equal_nan=True)
+    # the oracle as the judge of the sharded result
+    model = pd.newPsydiff(**synth.config_c4(N=64, T=16))
+    pd.compileModel(model)
+    pd.setDevices(model, nd)
+    _check_fit(model)
+    _check_grad(model, extended=True)

@@ -472,3 +472,60 @@ def test_reduction_kernels_k3_on_the_cpu():
     assert np.allclose(part[fin], want[fin], rtol=1e-12, atol=1e-9)                     # sums to rounding (different tree)
     assert not np.isfinite(part[0]) and part[1] >= 2                                    # Σ f0 carries the failed base instances, counted
     assert part[2 + 4 * P + 0] == part[1]                                               # nbt of a common parameter = all failed persons
+
+
+def test_builder_kernels_k2_on_the_cpu():
+    """psy_k2.cuh (K2) compiled for the host and run in psy_capi.cu's launch order: the device-built instance list, pair lists,
+    segment offsets and chunk / small / big lists equal the plain restatement (k3sim.lists) entry for entry — common, group and
+    person-specific parameters, a repeated label, more persons than one layout chunk (1024) and than one K3 chunk (4096); the
+    selection predicate of restricted sweeps; the per-set reduction of psy_fit_many; the RK4 step counts against the host rule."""
+    from hostsim import k2sim, k3sim
+    from psydiff_b200 import _lib
+    rng = np.random.default_rng(3)
+    for N, F in ((5000, 6), (37, 3), (1, 1), (2100, 40)):
+        n_common, n_group = min(3, F), 5
+        P = n_common + n_group + N
+        tidx = np.empty((N, F), dtype=np.int32)
+        tidx[:, :n_common] = np.arange(n_common)
+        for k in range(n_common, F):
+            tidx[:, k] = n_common + rng.integers(0, n_group, N)
+        if F > 4:
+            tidx[:, 4] = tidx[:, 3]                      # the same label in two slots: one pair per person
+            tidx[:, F - 1] = n_common + n_group + np.arange(N)
+        if F == 40:
+            tidx[:, 5:20] = (n_common + n_group + np.arange(N))[:, None]   # 61-slot blocks vs 19-slot ones: aligned and packed persons mix
+            tidx[::3, 5:20] = tidx[::3, 3:4]
+        a, b = k2sim.build(tidx, P), k3sim.lists(tidx, P)
+        for key in ("n_inst", "start", "pair_minus", "pair_base", "seg_off", "chunks", "tco", "small", "big"):
+            assert np.array_equal(np.asarray(a[key]), np.asarray(b[key])), (N, F, key)
+        inst = a["inst"]
+        for p in (0, N // 2, N - 1):
+            o = int(b["start"][p])
+            assert tuple(inst[o]) == (p, -1) and tuple(a["base"][p]) == (p, -1)
+            for j, t in enumerate(b["distinct"][p]):
+                assert tuple(inst[o + 1 + 2 * j]) == (p, 2 * t) and tuple(inst[o + 2 + 2 * j]) == (p, 2 * t + 1)
+        real = inst[:, 0] >= 0
+        assert real.sum() == N + 2 * sum(len(d) for d in b["distinct"]) and np.all(inst[~real] == -1)       # the rest is padding
+        # restricted sweeps: a one-sided first level (base + that side), then an eps[] fallback level for two (theta, side) pairs
+        sel = k2sim.select(inst, None, 1, 1, 0)
+        assert np.array_equal(sel, np.flatnonzero(real & ((inst[:, 1] < 0) | (inst[:, 1] % 2 == 0))))
+        need = np.zeros(2 * P, dtype=np.uint8)
+        need[[1, 2 * (n_common + 1)]] = 1
+        sel = k2sim.select(inst, need, 0, 1, 1)
+        assert np.array_equal(sel, np.flatnonzero(real & (inst[:, 1] >= 0) & np.isin(inst[:, 1], [1, 2 * (n_common + 1)])))
+    # psy_fit_many's reduction: per parameter set, Σ of the non-NaN -2LL and the NaN count
+    N, K = 9001, 3
+    f = rng.standard_normal(K * N) + 40
+    f[[5, N + 7, N + 4100]] = np.nan
+    f[2 * N + 11] = np.inf
+    tot, bad = k2sim.sets(f, N, K)
+    fk = f.reshape(K, N)
+    assert np.array_equal(bad, [1, 2, 0]) and np.isinf(tot[2])
+    assert np.allclose(tot[:2], [np.nansum(fk[0]), np.nansum(fk[1])], rtol=1e-13)
+    # rule T1 on the device = the host's psy_rk4_step_count, on intervals around multiples of h and odd values
+    L = _lib.lib()
+    h = 1.0 / 30
+    dt = np.concatenate([np.arange(0, 40) * h, np.arange(1, 40) * h * (1 + 2e-16), np.arange(1, 40) * h * (1 - 2e-16),
+                         rng.random(500) * 3, [0.0, -1.0, np.nan, 1e-300, h / 2, 1e4]])
+    dev = k2sim.step_counts(dt, h)
+    assert np.array_equal(dev, [L.psy_rk4_step_count(float(d), h) for d in dt])

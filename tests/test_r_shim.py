@@ -145,7 +145,7 @@ def test_registration_table_matches_the_reference(r):
     for name, arity in REFERENCE_TABLE.items():
         assert got.get(name) == arity, name
     assert set(got) - set(REFERENCE_TABLE) == {"R_psy_emit_source", "R_psy_compile", "R_psy_is_current", "R_psy_upload", "R_psy_load_module",
-                                               "R_psy_fit", "R_psy_gradients", "R_psy_gradient"}
+                                               "R_psy_set_devices", "R_psy_fit", "R_psy_gradients", "R_psy_gradient"}
     assert r.L.psy_rstub_dynamic_symbols() == 0          # R_useDynamicSymbols(dll, FALSE), src/RcppExports.cpp:320
     with pytest.raises(RuntimeError, match="Incorrect number of arguments"):
         r.call("_psydiff_getPhi", r.num(np.eye(2)), r.num([1.0]))
@@ -368,6 +368,17 @@ def test_compile_sync_fit_gradient_flow_with_a_mock_device():
         r.call("R_psy_gradients", h, *settings, theta, r.num(model["eps"]), r.int([7]))
     with pytest.raises(RuntimeError, match="parameter index out of range"):
         r.call("R_psy_gradient", h, *settings, theta, r.int([999]), r.num(model["eps"]), r.int([0]))
+    # compileParallelGradients(model, nCores): the workers are devices of the handle — capped at the visible ones (4 in the mock)
+    assert list(r.py(r.call("R_psy_set_devices", h, r.int([2])))) == [0, 1]
+    assert list(r.py(r.call("R_psy_set_devices", h, r.int([64])))) == [0, 1, 2, 3]
+    assert list(r.py(r.call("R_psy_set_devices", h, r.int([0])))) == [0]                  # stopParallelGradients: back to one
+    # a changed integrateFunction / srUpdate: .psy_variant_sync hands the regenerated source to R_psy_load_module
+    L.psy_mock_module_loads.restype = C.c_int
+    L.psy_mock_module_loads.argtypes = [C.c_void_p]
+    model["integrateFunction"] = "runge_kutta_dopri5"
+    pd.model._sync_source(model)
+    r.call("R_psy_load_module", h, r.chr(model["cppCode"]), r.chr(_lib.CSRC_DIR), r.chr(_lib.CACHE_DIR))
+    assert L.psy_mock_module_loads(r.L.R_ExternalPtrAddr(h)) == 1
     # a different model object of the same structure: re-upload, results follow the new data; handing the first one back re-uploads again
     model2 = pd.newPsydiff(**synth.config_c4(N=4, T=6, seed=77))
     rm2 = _r_model(r, model2)
@@ -418,3 +429,30 @@ def test_compile_fit_and_gradients_through_the_shim_on_the_gpu(r):
     assert not r.L.R_ExternalPtrAddr(h)
     with pytest.raises(RuntimeError, match="model is not compiled"):
         r.call("R_psy_gradients", h, *settings, theta, r.num(model["eps"]), r.int([0]))
+
+
+@pytest.mark.gpu
+def test_get_gradients_parallel_through_the_shim_uses_several_gpus(r):
+    """compileParallelGradients / getGradientsParallel of r/psydiff_b200.R on a box with >= 2 GPUs: R_psy_set_devices spreads the
+    handle's persons over the devices; fit, states and gradient through the .Call interface equal the one-device results
+    (per-person values exactly, parameter sums to 1e-12) — no Python, no process per GPU."""
+    if pd.deviceCount() < 2:
+        pytest.skip("needs at least two GPUs")
+    model = pd.newPsydiff(**synth.config_c4(N=301, T=12))
+    h = _compile(r, model)
+    rm = _r_model(r, model)
+    settings = (r.num([model["alpha"], model["beta"], model["kappa"]]), r.int([0]), r.num(model["timeStep"]), r.lgl(True))
+    theta = r.call("_psydiff_getParameterValues", rm)
+    assert _sync(r, h, rm, model) is True
+    one = r.py(r.call("R_psy_fit", h, rm, *settings, theta, r.lgl(False)))
+    g1 = r.py(r.call("R_psy_gradients", h, *settings, theta, r.num(model["eps"]), r.int([0])))
+    n = min(pd.deviceCount(), 8)
+    assert list(r.py(r.call("R_psy_set_devices", h, r.int([n])))) == list(range(n))
+    many = r.py(r.call("R_psy_fit", h, rm, *settings, theta, r.lgl(False)))
+    gn = r.py(r.call("R_psy_gradients", h, *settings, theta, r.num(model["eps"]), r.int([0])))
+    for k in ("m2LL", "latentScores", "predictedManifest"):
+        assert np.array_equal(one[k], many[k]), k
+    assert np.max(np.abs(gn - g1) / np.maximum(np.abs(g1), 1e-300)) < 1e-12
+    assert list(r.py(r.call("R_psy_set_devices", h, r.int([1])))) == [0]
+    assert np.array_equal(r.py(r.call("R_psy_gradients", h, *settings, theta, r.num(model["eps"]), r.int([0]))), g1)
+    r.L.psy_rstub_run_finalizer(h)
