@@ -37,14 +37,14 @@
 #define PSY_BLOCK 0   // 0 = by model size: 64 threads, 32 for N >= 7 (Filter::BLOCK)
 #endif
 #ifndef PSY_MIN_BLOCKS
-#define PSY_MIN_BLOCKS 1
+#define PSY_MIN_BLOCKS 0  // 0 = by model (Filter::MIN_BLOCKS): 8 for the n <= 2 dopri5 kernel (128 registers), else 1
 #endif
 #ifndef PSY_RHS_SCALED
 #define PSY_RHS_SCALED 1
 #endif
 #ifndef PSY_RHS_FUSED
-#define PSY_RHS_FUSED 0   // only meaningful with PSY_RHS_SCALED: diffusion term folded into the triangular product (rhs_fused)
-#endif
+#define PSY_RHS_FUSED 1   // only meaningful with PSY_RHS_SCALED: diffusion term folded into the triangular product (rhs_fused);
+#endif                    // timed on B200 (profiles/r02c_variants.txt): C4 610.8 -> 604.8 ms, n = 8 734.4 -> 709.5 ms
 #ifndef PSY_RHS_STREAM
 #define PSY_RHS_STREAM 0  // small-live-set ordering of rhs_scaled (rhs_stream)
 #endif
@@ -114,7 +114,11 @@ struct Filter {
   // beside the RK4 parking area (L1 hit rate of spill loads 50 %, spill stores written through to L2 at 3.7 TB/s: 807 ms), 4 warps
   // with a 45 % shared-memory carveout keep the frame L1-resident (776 ms), and one-warp blocks schedule best (736 ms).
   static constexpr bool RSQ_ROT = (PSY_RSQRT_ROT == 1) || (PSY_RSQRT_ROT == -1 && Mdl::N <= 6);
-  static constexpr int BLOCK = (PSY_BLOCK > 0) ? PSY_BLOCK : ((N >= 7) ? 32 : 64);
+  // (n = 10: 64-thread blocks again, 3324 -> 3063 ms, profiles/r02c_variants.txt)
+  static constexpr int BLOCK = (PSY_BLOCK > 0) ? PSY_BLOCK : ((N >= 7 && N <= 8) ? 32 : 64);
+  // Resident blocks the register allocation is capped for.  The n <= 2 adaptive kernel (C3) is latency bound (divergent step-size
+  // control): 128 registers / 16 warps per SM instead of 204 / 8 measured 139.2 -> 112.9 ms on B200 (profiles/r02c_variants.txt).
+  static constexpr int MIN_BLOCKS = (PSY_MIN_BLOCKS > 0) ? PSY_MIN_BLOCKS : ((Mdl::STEPPER == 1 && N <= 2) ? 512 / BLOCK : 1);
   static constexpr int SMEM_CARVEOUT_PCT = (N >= 7) ? 45 : -1;   // preferred shared-memory carveout (percent of the maximum), -1 = driver's choice
 
   struct UT { double sqrtc, wm0, wm1, wc0, wc1, kap; };
@@ -1142,6 +1146,50 @@ struct Filter {
     return (double)z.o * 1.8378770664093453 + 2.0 * ld + dist;
   }
 
+  // ---- prologue pieces shared with the lane-pair kernel (psy_filter_pair.cuh) -----------------------------------------
+  // free-slot values of an instance: theta gathered through the person's slot map, one entry shifted by ±eps
+  // (setParameterValues_C + setParameterList_C, inst/include/psydiffBasic.h:4-33, 63-121, stateless — quirk Q4)
+  static __device__ __forceinline__ void gather(const PsyLaunch& L, const PsyInst& in, double (&p)[F]) {
+    const int* ti = L.theta_index + (size_t)in.person * Mdl::NSLOT;
+    const double* th = L.theta + ((in.code < -1) ? (size_t)(-1 - in.code) * (size_t)L.n_theta : (size_t)0);
+    const int pert = (in.code >= 0) ? (in.code >> 1) : -1;
+    const double sh = (in.code & 1) ? L.eps : -L.eps;
+#pragma unroll
+    for (int k = 0; k < F; k++) p[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < Mdl::NSLOT; k++) {
+      const int t = __ldg(ti + k);
+      double v = __ldg(th + t);
+      if (t == pert) v += sh;
+      p[k] = v;
+    }
+  }
+  // m0, A0 = logChol2Chol(A0LogChol), Q = Q_SCALE · L Lᵀ with L = logChol2Chol(LLogChol)  (R/modelTemplate.R:275-276, 81)
+  static __device__ __forceinline__ void initial_state(const double (&p)[F], double (&m)[N], double (&A)[TN], double (&Q)[QLEN]) {
+    double A0[N * N], Ll[N * N];
+    Mdl::initial(m, A0, Ll, p);
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+      for (int j = 0; j <= i; j++) A[tri(i, j)] = (i == j) ? exp(A0[i + j * N]) : A0[i + j * N];  // logChol2Chol_C
+    if constexpr (Mdl::L_STRUCT == L_DIAG) {
+#pragma unroll
+      for (int k = 0; k < N; k++) { const double l = exp(Ll[k + k * N]); Q[k] = Q_SCALE * (l * l); }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; i++) Ll[i + i * N] = exp(Ll[i + i * N]);
+#pragma unroll
+      for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < N; k++) acc += Ll[i + k * N] * Ll[j + k * N];
+          Q[tri(i, j)] = Q_SCALE * acc;
+        }
+    }
+  }
+
   // ---- one instance through all of its person's time points ------------------------------------------------
   static __device__ __forceinline__ void run(const PsyLaunch& L) {
     const int ii = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1149,54 +1197,15 @@ struct Filter {
     const PsyInst in = L.inst[ii];
     const int person = in.person;
     if (person < 0) return;  // warp-alignment padding slot
-    // free-slot values of this instance: theta gathered through the person's slot map, one entry shifted by ±eps
-    // (setParameterValues_C + setParameterList_C, inst/include/psydiffBasic.h:4-33, 63-121, stateless — quirk Q4)
     double p[F];
-    {
-      const int* ti = L.theta_index + (size_t)person * Mdl::NSLOT;
-      const double* th = L.theta + ((in.code < -1) ? (size_t)(-1 - in.code) * (size_t)L.n_theta : (size_t)0);
-      const int pert = (in.code >= 0) ? (in.code >> 1) : -1;
-      const double sh = (in.code & 1) ? L.eps : -L.eps;
-#pragma unroll
-      for (int k = 0; k < F; k++) p[k] = 0.0;
-#pragma unroll
-      for (int k = 0; k < Mdl::NSLOT; k++) {
-        const int t = __ldg(ti + k);
-        double v = __ldg(th + t);
-        if (t == pert) v += sh;
-        p[k] = v;
-      }
-    }
+    gather(L, in, p);
     UT ut;
     ut.sqrtc = L.sqrtc; ut.wm0 = L.wm0; ut.wm1 = L.wm1; ut.wc0 = L.wc0; ut.wc1 = L.wc1;
     ut.kap = L.wc1 * L.sqrtc;
     const int pid = __ldg(L.person_id + person);
 
     double m[N], A[TN], Q[QLEN];
-    {
-      double A0[N * N], Ll[N * N];
-      Mdl::initial(m, A0, Ll, p);  // m0, A0LogChol, LLogChol entries (R/modelTemplate.R:275-276, 81)
-#pragma unroll
-      for (int i = 0; i < N; i++)
-#pragma unroll
-        for (int j = 0; j <= i; j++) A[tri(i, j)] = (i == j) ? exp(A0[i + j * N]) : A0[i + j * N];  // logChol2Chol_C
-      if constexpr (Mdl::L_STRUCT == L_DIAG) {
-#pragma unroll
-        for (int k = 0; k < N; k++) { const double l = exp(Ll[k + k * N]); Q[k] = Q_SCALE * (l * l); }
-      } else {
-#pragma unroll
-        for (int i = 0; i < N; i++) Ll[i + i * N] = exp(Ll[i + i * N]);
-#pragma unroll
-        for (int i = 0; i < N; i++)
-#pragma unroll
-          for (int j = 0; j <= i; j++) {
-            double acc = 0.0;
-#pragma unroll
-            for (int k = 0; k < N; k++) acc += Ll[i + k * N] * Ll[j + k * N];
-            Q[tri(i, j)] = Q_SCALE * acc;
-          }
-      }
-    }
+    initial_state(p, m, A, Q);
     const long long r0 = __ldg(L.row_off + person);
     const int T = (int)(__ldg(L.row_off + person + 1) - r0);
     const bool base = (in.code == -1);
@@ -1296,6 +1305,6 @@ struct Filter {
                                                         MODEL::STEPPER == 0 ? psy::Filter<MODEL>::SMEM_CARVEOUT_PCT : -1,    \
                                                         psy::Filter<MODEL>::BLOCK};                                          \
   static constexpr int psy_block_size = psy::Filter<MODEL>::BLOCK;                                                 \
-  extern "C" __global__ void __launch_bounds__(psy::Filter<MODEL>::BLOCK, PSY_MIN_BLOCKS) psy_filter_kernel(const PsyLaunch L) {   \
+  extern "C" __global__ void __launch_bounds__(psy::Filter<MODEL>::BLOCK, psy::Filter<MODEL>::MIN_BLOCKS) psy_filter_kernel(const PsyLaunch L) {   \
     psy::Filter<MODEL>::run(L);                                                                                     \
   }

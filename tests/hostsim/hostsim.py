@@ -70,17 +70,17 @@ def build(source: str, extra_flags: str = "") -> str:
     so = os.path.join(_BUILD, f"sim_{key}.so")
     if not os.path.exists(so):
         os.makedirs(_BUILD, exist_ok=True)
-        cpp = os.path.join(_BUILD, f"sim_{key}.cpp")
+        cpp = os.path.join(_BUILD, f"sim_{key}_{os.getpid()}.cpp")   # per process: pytest-xdist workers may build the same model
         with open(cpp, "w") as f:
             f.write('#include "cuda_host_shim.h"\n' + source + _DRIVER)
         # -ffp-contract=fast + -mfma: a*b+c contracts to fma like nvcc's default -fmad=true (not necessarily the same
         # choices: agreement with the device is to rounding, not bit for bit)
         cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-mfma", "-ffp-contract=fast", "-Wno-unknown-pragmas",
-               "-I", _HERE, "-I", _CSRC] + extra_flags.split() + ["-o", so + ".tmp", cpp]
+               "-I", _HERE, "-I", _CSRC] + extra_flags.split() + ["-o", so + f".tmp{os.getpid()}", cpp]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("hostsim: g++ failed:\n" + r.stderr[:4000])
-        os.replace(so + ".tmp", so)
+        os.replace(so + f".tmp{os.getpid()}", so)
     return so
 
 
