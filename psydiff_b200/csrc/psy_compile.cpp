@@ -152,7 +152,7 @@ int psy_model_compile(const char* cuda_source, const char* include_dir, const ch
   if (!cuda_source || !include_dir || !cache_dir || !cubin_path) return fail(PSY_ERR_ARG, "psy_model_compile: null argument");
   const std::string inc(include_dir), cache(cache_dir), flags(extra_flags ? extra_flags : "");
   uint64_t h = fnv1a(cuda_source);
-  for (const char* hdr : {"/psy_filter.cuh", "/psy_lang.cuh", "/psy_launch.h"}) {
+  for (const char* hdr : {"/psy_filter.cuh", "/psy_filter_pair.cuh", "/psy_lang.cuh", "/psy_launch.h"}) {
     std::string body = slurp(inc + hdr);
     if (body.empty()) return fail(PSY_ERR_COMPILE, "kernel header %s%s not found", include_dir, hdr);
     h = fnv1a(body, h);

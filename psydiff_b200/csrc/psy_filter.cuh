@@ -1297,14 +1297,34 @@ struct Filter {
 
 }  // namespace psy
 
+#include "psy_filter_pair.cuh"
+
+namespace psy {
+// the kernel a model gets: the lane-pair form where it is eligible and enabled (psy_filter_pair.cuh), else one thread per instance
+template <class Mdl>
+struct Kernel {
+  using P = FilterPair<Mdl>;
+  using S = Filter<Mdl>;
+  static constexpr bool PAIR = P::ENABLED;
+  static constexpr int BLOCK = PAIR ? P::BLOCK : S::BLOCK;
+  static constexpr int MIN_BLOCKS = PAIR ? 1 : S::MIN_BLOCKS;
+  static constexpr int SMEM_BYTES = PAIR ? P::SMEM_BYTES : (Mdl::STEPPER == 0 ? S::SMEM_BYTES : 0);
+  static constexpr int SMEM_CARVEOUT_PCT = PAIR ? P::SMEM_CARVEOUT_PCT : (Mdl::STEPPER == 0 ? S::SMEM_CARVEOUT_PCT : -1);
+  static __device__ __forceinline__ void run(const PsyLaunch& L) {
+    if constexpr (PAIR) P::run(L);
+    else S::run(L);
+  }
+};
+}  // namespace psy
+
 // psy_module_info = {stepper, srUpdate, nlatent, nmanifest, free slots, dynamic shared memory bytes, preferred shared-memory carveout in
 // percent (-1 = the driver's choice), threads per block}: lets the host check a module against its settings and launch it as it was built
 #define PSY_INSTANTIATE(MODEL)                                                                                      \
   extern "C" __device__ const int psy_module_info[8] = {MODEL::STEPPER, MODEL::SR ? 1 : 0, MODEL::N, MODEL::M, MODEL::NSLOT, \
-                                                        MODEL::STEPPER == 0 ? psy::Filter<MODEL>::SMEM_BYTES : 0,            \
-                                                        MODEL::STEPPER == 0 ? psy::Filter<MODEL>::SMEM_CARVEOUT_PCT : -1,    \
-                                                        psy::Filter<MODEL>::BLOCK};                                          \
-  static constexpr int psy_block_size = psy::Filter<MODEL>::BLOCK;                                                 \
-  extern "C" __global__ void __launch_bounds__(psy::Filter<MODEL>::BLOCK, psy::Filter<MODEL>::MIN_BLOCKS) psy_filter_kernel(const PsyLaunch L) {   \
-    psy::Filter<MODEL>::run(L);                                                                                     \
+                                                        psy::Kernel<MODEL>::SMEM_BYTES, psy::Kernel<MODEL>::SMEM_CARVEOUT_PCT,  \
+                                                        psy::Kernel<MODEL>::BLOCK};                                          \
+  static constexpr int psy_block_size = psy::Kernel<MODEL>::BLOCK;                                                 \
+  static constexpr int psy_lanes_per_instance_in_rk4 = psy::Kernel<MODEL>::PAIR ? 2 : 1;                           \
+  extern "C" __global__ void __launch_bounds__(psy::Kernel<MODEL>::BLOCK, psy::Kernel<MODEL>::MIN_BLOCKS) psy_filter_kernel(const PsyLaunch L) {   \
+    psy::Kernel<MODEL>::run(L);                                                                                     \
   }

@@ -36,6 +36,9 @@
 #ifndef PSY_PAIR_BLOCK
 #define PSY_PAIR_BLOCK 64
 #endif
+#ifndef PSY_PAIR_DIRECT
+#define PSY_PAIR_DIRECT 0   // 1: both lanes fetch Ã's even / odd columns with source-lane shuffles (2 per entry, no selects)
+#endif
 #ifndef PSY_PAIR_CARVEOUT
 #define PSY_PAIR_CARVEOUT (-1)
 #endif
@@ -65,7 +68,10 @@ struct FilterPair {
   static constexpr int BLOCK = PSY_PAIR_BLOCK;
   static constexpr int PARK = PSY_PAIR_PARK;
   static constexpr int SMEM_BYTES = PARK * NS * BLOCK * 8;
-  static constexpr int SMEM_CARVEOUT_PCT = PSY_PAIR_CARVEOUT;
+  // shared-memory carveout (percent of 228 KB) that lets the 65536 / (256 · BLOCK) blocks the register file holds be resident
+  static constexpr int RESIDENT_BLOCKS = 256 / BLOCK;
+  static constexpr int SMEM_CARVEOUT_PCT = (PSY_PAIR_CARVEOUT >= 0) ? PSY_PAIR_CARVEOUT
+      : (PARK == 0 ? -1 : (100 * RESIDENT_BLOCKS * (SMEM_BYTES + 1024) + 233471) / 233472);
   __host__ __device__ static constexpr int off(int c) { return c * N - c * (c - 1); }   // first entry of column pair c (row 2c)
   __host__ __device__ static constexpr int woff(int c) { return c * (c + 1); }          // first entry of the own W row of pair c
   // index of Ã(i, j), i > j, in the even (j = 2c) / odd (j = 2c+1) column views
@@ -87,16 +93,20 @@ struct FilterPair {
 #pragma unroll
       for (int k = 1; k < N - 2 * c; k++) {
         const double own = Ac[off(c) + k] * rdj[c];
+#if PSY_PAIR_DIRECT
+        E[off(c) + k] = lane_from(own, lane_id() & ~1);
+        if (k > 1) O[off(c) + k] = lane_from(own, lane_id() | 1);
+#else
         const double oth = lane_xchg(own);
         E[off(c) + k] = r ? oth : own;
         O[off(c) + k] = r ? own : oth;   // k = 1 is the odd column's diagonal (≈ 1, never read)
+#endif
       }
 #define PSY_AT(i, j) ((((j) & 1) ? O : E)[ati((i), (j))])
     // own row j = 2c + r of W = Ã⁻¹ by back substitution of e_jᵀ = wᵀ Ã over the rows 0..2c+1 (entries above j come out as 0)
     double w[TW];
 #pragma unroll
     for (int c = 0; c < NP; c++) {
-      constexpr int dummy = 0; (void)dummy;
       const int R = 2 * c + 1;
       w[woff(c) + R] = r ? 1.0 : 0.0;
       w[woff(c) + R - 1] = r ? -PSY_AT(R, R - 1) : 1.0;
@@ -206,13 +216,9 @@ struct FilterPair {
   // count Kmax so that the shuffles stay warp-uniform, a pair past its own K recomputes and restores its state.
   static __device__ __forceinline__ void rk4_pair(const double (&p)[F], double (&m)[N], double (&Ac)[TP], const double (&QH)[N],
                                                   const UT& ut, int person, double h, int K, int Kmax, const bool r) {
-#ifdef PSY_SIM_WARP
-    double* const psy_smem_ = psy_sim_smem();
-#else
-    extern __shared__ double psy_smem_[];
-#endif
-    volatile double* sx = psy_smem_ + threadIdx.x;                                  // x_n : sx[e * BLOCK]  (PARK >= 1)
-    volatile double* sa = psy_smem_ + (PARK >= 2 ? NS * BLOCK : 0) + threadIdx.x;   // sum : sa[e * BLOCK]  (PARK == 2)
+    extern __shared__ double psy_smem[];
+    volatile double* sx = psy_smem + threadIdx.x;                                  // x_n : sx[e * BLOCK]  (PARK >= 1)
+    volatile double* sa = psy_smem + (PARK >= 2 ? NS * BLOCK : 0) + threadIdx.x;   // sum : sa[e * BLOCK]  (PARK == 2)
 #pragma unroll 1
     for (int step = 0; step < Kmax; step++) {
       const double t0 = (double)step * h;

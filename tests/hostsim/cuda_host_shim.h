@@ -54,4 +54,53 @@ static inline double psy_sim_rsqrt_seed(double x) {
 #include "op_counter.h"     // from here on `double` is the counting wrapper (sizeof 8, same layout): the kernel source below counts its flops
 #endif
 
-namespace psy { double psy_smem[1 << 14]; }  // dynamic shared memory of the ONE simulated thread block (single host thread)
+namespace psy { double psy_smem[1 << 14]; }  // dynamic shared memory of the ONE simulated thread block
+
+// Warp collectives of the lane-pair kernel (psy_filter_pair.cuh): a simulated warp is PSY_SIM_WARP host threads that really run
+// concurrently; a shuffle is "publish my value, barrier, read the source lane's, barrier".  The kernel only uses lane ^ 1,
+// lane & ~1, lane | 1 as sources and whole-warp maxima, so any even width is equivalent to 32.
+#ifndef PSY_SIM_WARP
+#define PSY_SIM_WARP 4
+#endif
+#include <atomic>
+struct psy_sim_warp_state {
+  std::atomic<int> arrived{0};
+  std::atomic<int> sense{0};
+  unsigned long long box[PSY_SIM_WARP];
+};
+static psy_sim_warp_state psy_sim_ws;
+static thread_local int psy_sim_lane = 0, psy_sim_local_sense = 0;
+static inline void psy_sim_warp_barrier() {
+  psy_sim_local_sense ^= 1;
+  if (psy_sim_ws.arrived.fetch_add(1, std::memory_order_acq_rel) == PSY_SIM_WARP - 1) {
+    psy_sim_ws.arrived.store(0, std::memory_order_relaxed);
+    psy_sim_ws.sense.store(psy_sim_local_sense, std::memory_order_release);
+  } else {
+    while (psy_sim_ws.sense.load(std::memory_order_acquire) != psy_sim_local_sense) {}
+  }
+}
+template <class T>
+static inline T psy_sim_shfl(T v, int src) {
+  static_assert(sizeof(T) <= 8, "");
+  unsigned long long b = 0;
+  memcpy(&b, &v, sizeof v);
+  psy_sim_ws.box[psy_sim_lane] = b;
+  psy_sim_warp_barrier();
+  b = psy_sim_ws.box[src];
+  psy_sim_warp_barrier();
+  T out;
+  memcpy(&out, &b, sizeof out);
+  return out;
+}
+namespace psy {
+static inline double lane_xchg(double v) { return psy_sim_shfl(v, psy_sim_lane ^ 1); }
+static inline double lane_from(double v, int src) { return psy_sim_shfl(v, src); }
+static inline int lane_from(int v, int src) { return psy_sim_shfl(v, src); }
+static inline int warp_max(int v) {
+  int mx = v;
+  for (int l = 0; l < PSY_SIM_WARP; l++) { const int o = psy_sim_shfl(v, l); mx = o > mx ? o : mx; }
+  return mx;
+}
+static inline void warp_sync() { psy_sim_warp_barrier(); }
+static inline int lane_id() { return psy_sim_lane; }
+}  // namespace psy

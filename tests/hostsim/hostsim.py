@@ -23,18 +23,41 @@ _CSRC = os.path.join(_ROOT, "psydiff_b200", "csrc")
 _BUILD = os.path.join(_HERE, "_build")
 
 _DRIVER = r"""
+#include <thread>
+#include <vector>
 extern "C" void psy_hostsim_run(const PsyLaunch* L, int block) {
   const int grid = (L->n_inst + block - 1) / block;
-  blockDim.x = (unsigned)block; blockDim.y = blockDim.z = 1;
-  gridDim.x = (unsigned)grid; gridDim.y = gridDim.z = 1;
+  if (psy_lanes_per_instance_in_rk4 == 1) {
+    blockDim.x = (unsigned)block; blockDim.y = blockDim.z = 1;
+    gridDim.x = (unsigned)grid; gridDim.y = gridDim.z = 1;
+    for (int b = 0; b < grid; b++)
+      for (int t = 0; t < block; t++) {
+        blockIdx.x = (unsigned)b; blockIdx.y = blockIdx.z = 0;
+        threadIdx.x = (unsigned)t; threadIdx.y = threadIdx.z = 0;
+        psy_filter_kernel(*L);
+      }
+    return;
+  }
+  // lane-pair kernel: one simulated warp (PSY_SIM_WARP concurrent host threads, cuda_host_shim.h) at a time; warps that hold no
+  // instance are skipped (they would only compute on zeros)
   for (int b = 0; b < grid; b++)
-    for (int t = 0; t < block; t++) {
-      blockIdx.x = (unsigned)b; blockIdx.y = blockIdx.z = 0;
-      threadIdx.x = (unsigned)t; threadIdx.y = threadIdx.z = 0;
-      psy_filter_kernel(*L);
+    for (int w0 = 0; w0 < block; w0 += PSY_SIM_WARP) {
+      if (b * block + w0 >= L->n_inst) continue;
+      std::vector<std::thread> th;
+      for (int l = 0; l < PSY_SIM_WARP; l++)
+        th.emplace_back([=] {
+          blockDim.x = (unsigned)block; blockDim.y = blockDim.z = 1;
+          gridDim.x = (unsigned)grid; gridDim.y = gridDim.z = 1;
+          blockIdx.x = (unsigned)b; blockIdx.y = blockIdx.z = 0;
+          threadIdx.x = (unsigned)(w0 + l); threadIdx.y = threadIdx.z = 0;
+          psy_sim_lane = l; psy_sim_local_sense = psy_sim_ws.sense.load();
+          psy_filter_kernel(*L);
+        });
+      for (auto& t : th) t.join();
     }
 }
 extern "C" int psy_hostsim_block(void) { return psy_block_size; }
+extern "C" int psy_hostsim_lanes(void) { return psy_lanes_per_instance_in_rk4; }
 #ifdef PSY_COUNT_OPS
 extern "C" void psy_hostsim_ops(unsigned long long* out, int reset) {
   out[0] = psy_ops::add; out[1] = psy_ops::mul; out[2] = psy_ops::fma_; out[3] = psy_ops::div_; out[4] = psy_ops::special;
@@ -64,7 +87,7 @@ def _ptr(a):
 
 def build(source: str, extra_flags: str = "") -> str:
     """g++-compile one model TU (+ the simulation driver) into tests/hostsim/_build/sim_<hash>.so."""
-    hdrs = "".join(open(os.path.join(_CSRC, h)).read() for h in ("psy_filter.cuh", "psy_lang.cuh", "psy_launch.h"))
+    hdrs = "".join(open(os.path.join(_CSRC, h)).read() for h in ("psy_filter.cuh", "psy_filter_pair.cuh", "psy_lang.cuh", "psy_launch.h"))
     shim = open(os.path.join(_HERE, "cuda_host_shim.h")).read()
     key = hashlib.sha1((source + hdrs + shim + _DRIVER + extra_flags).encode()).hexdigest()[:16]
     so = os.path.join(_BUILD, f"sim_{key}.so")
@@ -75,7 +98,7 @@ def build(source: str, extra_flags: str = "") -> str:
             f.write('#include "cuda_host_shim.h"\n' + source + _DRIVER)
         # -ffp-contract=fast + -mfma: a*b+c contracts to fma like nvcc's default -fmad=true (not necessarily the same
         # choices: agreement with the device is to rounding, not bit for bit)
-        cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-mfma", "-ffp-contract=fast", "-Wno-unknown-pragmas",
+        cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-mfma", "-ffp-contract=fast", "-Wno-unknown-pragmas", "-pthread",
                "-I", _HERE, "-I", _CSRC] + extra_flags.split() + ["-o", so + f".tmp{os.getpid()}", cpp]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -94,6 +117,7 @@ class HostSim:
         self.lib = C.CDLL(build(model["cppCode"], extra_flags))
         self.lib.psy_hostsim_info.restype = C.POINTER(C.c_int)
         self.block = int(self.lib.psy_hostsim_block())
+        self.lanes = int(self.lib.psy_hostsim_lanes())     # 2 = the lane-pair kernel (psy_filter_pair.cuh) is what was compiled
         info = self.lib.psy_hostsim_info()
         self.info = [int(info[i]) for i in range(6)]
         spec = model["_spec"]

@@ -158,6 +158,41 @@ def test_coupled_oscillator_family_n2_n8_n10(K):
         _check_grad(model, hs, extended=True)
 
 
+@pytest.mark.parametrize("K", [2, 3, 4])
+def test_lane_pair_kernel_ragged_unaligned_and_against_the_thread_per_instance_kernel(K):
+    """psy_filter_pair.cuh (two lanes integrate one instance, every lane owns one): persons of different length, series of one
+    row, irregular dt (pairs of one simulated warp need different step counts: the restore path), instance lists without warp
+    alignment, padding slots — against the oracle and against the thread-per-instance kernel, for every parking level."""
+    kw = synth.config_coupled(K=K, N=7, T=9, n_groups=2, seed=99 + K)
+    obs = kw["dataset"]["observations"]
+    keep = np.ones(len(obs), dtype=bool)
+    keep[1 * 9 + 4:2 * 9] = False              # person 1: 4 rows
+    keep[3 * 9 + 1:4 * 9] = False              # person 3: a single row (no integration at all)
+    keep[4 * 9 + 7:5 * 9] = False              # person 4: 7 rows
+    obs[5 * 9 + 2] = np.nan                    # a time point without observations
+    obs[2 * 9 + 3, 0] = np.nan
+    for k in ("person", "observations", "dt"):
+        kw["dataset"][k] = kw["dataset"][k][keep]
+    model = pd.newPsydiff(**kw)
+    hs, fit, _ = _check_fit(model, flags="-DPSY_PAIR=1")
+    assert hs.lanes == 2
+    one = HostSim(model, "-DPSY_PAIR=0")
+    assert one.lanes == 1
+    ref = one.gradients(pad=False)
+    for flags in ("-DPSY_PAIR=1 -DPSY_PAIR_PARK=0", "-DPSY_PAIR=1 -DPSY_PAIR_PARK=1", "-DPSY_PAIR=1 -DPSY_PAIR_PARK=2"):
+        for pad in (False, True):
+            g = HostSim(model, flags).gradients(pad=pad)
+            assert np.max(np.abs(g["m2LL"] - ref["m2LL"]) / np.abs(ref["m2LL"])) < 1e-12
+            fa = g["f"][np.isfinite(g["f"])] if pad else g["f"]
+            assert np.max(np.abs(fa - ref["f"]) / np.abs(ref["f"])) < 1e-12
+    # parameter sets (psy_fit_many) through the pair kernel
+    th = hs.theta()
+    sets = np.stack([th, th * 1.01])
+    many = hs.fit_many(sets)
+    for k in range(2):
+        assert np.array_equal(many[k], hs.fit(theta=sets[k], states=False)["m2LL"])
+
+
 def test_instance_list_padding_and_parameter_sets_do_not_change_results():
     """Warp-alignment padding slots (person = -1) are skipped, and instance results do not depend on where an instance sits:
     padded and unpadded lists give bit-identical numbers; psy_fit_many's set k equals psy_fit at thetas[k]."""
