@@ -299,9 +299,17 @@ def kernel_roofline(name, model, n_inst, n_persons, kernel_ms, peak, calib, T):
         out["flops_per_instance_loop_count"] = fl_formula
         out["flops_per_instance_survey_formula"] = flops.survey_flops(w["n"], w["m"], w["Ff"], w["Fh"], steps_pp, T)
     ent = calib.get(key)
+    lanes = int(L.psy_kernel_lanes(h.ptr))
+    out["lanes_per_instance_in_rk4"] = lanes
     if ent and ent.get("config") == name:
         fl = float(ent["flops_per_instance"])
         out["calibration"] = f"ncu counters of this kernel ({ent.get('source', CALIBRATION)})"
+        if lanes > 1 and fl_formula is not None:
+            # lane-pair kernel: the executed count includes the pair's redundant work (centre drift, mean update, padded columns);
+            # the roofline numerator is the ALGORITHMIC count of the thread-per-instance formulation
+            out["flops_per_instance_executed"] = fl
+            fl = fl_formula
+            out["calibration"] += "; lane-pair kernel: achieved/frac use the loop-count flops of the thread-per-instance formulation, not the executed count"
         out["traffic"] = float(ent["dram_bytes_per_person"]) * n_persons
         out["traffic_unit"] = "bytes/launch (ncu dram__bytes_read+write of the calibration launch of this kernel, per person x persons)"
         out["ncu_fp64_pipe_active_pct"] = ent.get("fp64_pipe_active_pct")

@@ -181,6 +181,9 @@ int64_t psy_n_instances(const psy_model* mdl);
 int psy_measure_fp64_peak(double* tflops);
 /* kernel resource usage of the loaded module */
 int psy_kernel_info(const psy_model* mdl, int* regs, int* local_bytes, int* max_threads);
+/* Lanes that share one filter instance in the RK4 stage loop of the loaded kernel: 1 = one thread per instance, 2 = the lane-pair
+   kernel (even n >= 8; every lane still owns one instance in the measurement update).  Diagnostics only; no reference counterpart. */
+int psy_kernel_lanes(const psy_model* mdl);
 
 /* ---- the filter primitives the reference exports to R one by one (src/exposeInlineFunctions.cpp:13-308,
  * R signatures in R/RcppExports.R:12-257).  Tiny host-side utilities on column-major buffers; they are NOT on

@@ -76,6 +76,7 @@ SIGNATURES = {
     "psy_n_instances": (C.c_int64, [C.c_void_p]),
     "psy_measure_fp64_peak": (C.c_int, [c_double_p]),
     "psy_kernel_info": (C.c_int, [C.c_void_p, c_int_p, c_int_p, c_int_p]),
+    "psy_kernel_lanes": (C.c_int, [C.c_void_p]),
     # primitives (src/exposeInlineFunctions.cpp)
     "psy_getMeanWeights": (None, [C.c_int, C.c_double, C.c_double, C.c_double, c_double_p]),
     "psy_getCovWeights": (None, [C.c_int, C.c_double, C.c_double, C.c_double, c_double_p]),

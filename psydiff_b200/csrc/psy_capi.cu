@@ -216,6 +216,7 @@ struct psy_model {
   std::string image;
   int block = 128;                  // = the module's __launch_bounds__ block size
   int smem_bytes = 0;               // dynamic shared memory the kernel asks for (psy_module_info[5])
+  int lanes = 1;                    // lanes per instance in the RK4 stage loop (psy_module_lanes; 2 = lane-pair kernel)
   int mod_stepper = 0, mod_sr = 1;  // what the loaded module was generated for (psy_module_info)
   // devices
   std::vector<int> devices;
@@ -275,6 +276,9 @@ int load_module_on(psy_model* M, Shard& s, const char* what) {
   if (s.mod) g_drv.ModuleUnload(s.mod);
   s.mod = mod; s.fn = fn;
   M->mod_stepper = info[0]; M->mod_sr = info[1]; M->smem_bytes = info[5];
+  M->lanes = 1;
+  if (g_drv.ModuleGetGlobal(&gp, &gs, mod, "psy_module_lanes") == CUDA_SUCCESS && gs == sizeof(int))
+    CU_TRY(cudaMemcpy(&M->lanes, (const void*)gp, sizeof(int), cudaMemcpyDeviceToHost));
   if (M->smem_bytes > 48 * 1024) {
     r = g_drv.FuncSetAttribute(s.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, M->smem_bytes);
     if (r != CUDA_SUCCESS) return fail(PSY_ERR_CUDA, "cannot reserve %d bytes of shared memory: %s", M->smem_bytes, cu_str(r));
@@ -1031,5 +1035,7 @@ int psy_kernel_info(const psy_model* M, int* regs, int* local_bytes, int* max_th
   if (max_threads) { g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_MAX_THREADS_PER_BLOCK, fn); *max_threads = v; }
   return PSY_OK;
 }
+
+int psy_kernel_lanes(const psy_model* M) { return M ? M->lanes : 0; }
 
 }  // extern "C"

@@ -1307,7 +1307,7 @@ struct Kernel {
   using S = Filter<Mdl>;
   static constexpr bool PAIR = P::ENABLED;
   static constexpr int BLOCK = PAIR ? P::BLOCK : S::BLOCK;
-  static constexpr int MIN_BLOCKS = PAIR ? 1 : S::MIN_BLOCKS;
+  static constexpr int MIN_BLOCKS = PAIR ? P::MIN_BLOCKS : S::MIN_BLOCKS;
   static constexpr int SMEM_BYTES = PAIR ? P::SMEM_BYTES : (Mdl::STEPPER == 0 ? S::SMEM_BYTES : 0);
   static constexpr int SMEM_CARVEOUT_PCT = PAIR ? P::SMEM_CARVEOUT_PCT : (Mdl::STEPPER == 0 ? S::SMEM_CARVEOUT_PCT : -1);
   static __device__ __forceinline__ void run(const PsyLaunch& L) {
@@ -1318,11 +1318,13 @@ struct Kernel {
 }  // namespace psy
 
 // psy_module_info = {stepper, srUpdate, nlatent, nmanifest, free slots, dynamic shared memory bytes, preferred shared-memory carveout in
-// percent (-1 = the driver's choice), threads per block}: lets the host check a module against its settings and launch it as it was built
+// percent (-1 = the driver's choice), threads per block}: lets the host check a module against its settings and launch it as it was built;
+// psy_module_lanes = lanes that integrate one instance in the RK4 stage loop (2 = the lane-pair kernel, psy_filter_pair.cuh)
 #define PSY_INSTANTIATE(MODEL)                                                                                      \
   extern "C" __device__ const int psy_module_info[8] = {MODEL::STEPPER, MODEL::SR ? 1 : 0, MODEL::N, MODEL::M, MODEL::NSLOT, \
                                                         psy::Kernel<MODEL>::SMEM_BYTES, psy::Kernel<MODEL>::SMEM_CARVEOUT_PCT,  \
                                                         psy::Kernel<MODEL>::BLOCK};                                          \
+  extern "C" __device__ const int psy_module_lanes = psy::Kernel<MODEL>::PAIR ? 2 : 1;                             \
   static constexpr int psy_block_size = psy::Kernel<MODEL>::BLOCK;                                                 \
   static constexpr int psy_lanes_per_instance_in_rk4 = psy::Kernel<MODEL>::PAIR ? 2 : 1;                           \
   extern "C" __global__ void __launch_bounds__(psy::Kernel<MODEL>::BLOCK, psy::Kernel<MODEL>::MIN_BLOCKS) psy_filter_kernel(const PsyLaunch L) {   \

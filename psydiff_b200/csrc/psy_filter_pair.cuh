@@ -19,9 +19,14 @@
 //   H_j = Ã⁻¹ D'_j by forward substitution with Ã (no W), Σ (f+ + f−) all-reduced with one shuffle per component
 //   Phi(M̃)_ij = H_ij + H_ji: 2 x 2 block transposes across the pair (one shuffle per block)
 //   dA_j = Ã Phi_j (own columns), D⁻¹ folded into the RK4 coefficients.
-// Per stage and lane at n = 8: ≈ 780 FP64 instructions (half of the single-lane 1450 + 8 % redundancy: centre drift, m update,
-// padded structure), 34 double shuffles, ≈ 70 double selects; live state per lane ≈ half of the single-lane kernel's.
-// The step's start state x_n and the running RK4 sum can be parked in shared memory ([element][thread], conflict free).
+// Per stage and lane at n = 8 (SASS of the stage loop): 835 FP64 instructions against 1389 of the thread-per-instance kernel, i.e.
+// 20 % more arithmetic per instance (centre drift and mean update on both lanes, own-row recurrence of W, padded column structure),
+// 92 SHFL, 75 FSEL, 56 LDS + 28 STS, and NO local-memory traffic (thread-per-instance: 92 LDL + 78 STL + 88 LDS + 44 STS per stage).
+// The step's start state x_n and the running RK4 sum are parked in shared memory ([element][thread], conflict free).
+// Measured on B200 (profiles/r02d..g_pair_variants.txt, profiles/r02e_*): n = 10: 3156 -> 1216 ms (2.6x); n = 8: 1371 -> ≈ 1300 ms at
+// 4096 persons (FP64 pipe 52 % -> 65 % busy, which the 20 % extra arithmetic mostly eats); n = 6: 605 -> 841 ms and n = 4: 306 -> 463 ms
+// (441 FP64 instructions per lane against 665 / 2: the state fits one thread there, so the pair only adds redundancy) — hence
+// the default: pairs for even n >= 8 only.
 //
 // Control flow is kept WARP-uniform where shuffles are executed (full mask): time points run to the warp's longest series, the
 // step loop to the warp's largest step count, and lanes/pairs that are past their own end compute but do not commit.
@@ -31,13 +36,20 @@
 #define PSY_PAIR (-1)       // 1 = on where eligible, 0 = off, -1 = by model size (on for even n >= 8)
 #endif
 #ifndef PSY_PAIR_PARK
-#define PSY_PAIR_PARK 1     // RK4 vectors parked in shared memory: 0 none, 1 the step's start state x_n, 2 x_n and the running sum
+#define PSY_PAIR_PARK 2     // RK4 vectors parked in shared memory: 0 none, 1 the step's start state x_n, 2 x_n and the running sum
 #endif
 #ifndef PSY_PAIR_BLOCK
 #define PSY_PAIR_BLOCK 64
 #endif
 #ifndef PSY_PAIR_DIRECT
-#define PSY_PAIR_DIRECT 0   // 1: both lanes fetch Ã's even / odd columns with source-lane shuffles (2 per entry, no selects)
+#define PSY_PAIR_DIRECT 1   // 1: both lanes fetch Ã's even / odd columns with source-lane shuffles (2 per entry, no selects): 691.6 -> 681.6 ms
+#endif
+#ifndef PSY_PAIR_WORDER
+#define PSY_PAIR_WORDER 0   // 1: the dot products of the W-row recurrence take the newest entry last (shorter dependency chain on
+#endif                      // paper; measured SLOWER on B200: 702.0 vs 681.8 ms, profiles/r02g_pair_variants.txt)
+#ifndef PSY_PAIR_MIN_BLOCKS
+#define PSY_PAIR_MIN_BLOCKS 1   // resident blocks the register allocation is capped for (launch bounds); 168 registers (6 blocks,
+                                // 3 warps per scheduler) measured 841.6 ms against 681.8 ms at 255: the stage loop then spills 97 values
 #endif
 #ifndef PSY_PAIR_CARVEOUT
 #define PSY_PAIR_CARVEOUT (-1)
@@ -69,7 +81,8 @@ struct FilterPair {
   static constexpr int PARK = PSY_PAIR_PARK;
   static constexpr int SMEM_BYTES = PARK * NS * BLOCK * 8;
   // shared-memory carveout (percent of 228 KB) that lets the 65536 / (256 · BLOCK) blocks the register file holds be resident
-  static constexpr int RESIDENT_BLOCKS = 256 / BLOCK;
+  static constexpr int MIN_BLOCKS = PSY_PAIR_MIN_BLOCKS;
+  static constexpr int RESIDENT_BLOCKS = (MIN_BLOCKS > 256 / BLOCK) ? MIN_BLOCKS : 256 / BLOCK;
   static constexpr int SMEM_CARVEOUT_PCT = (PSY_PAIR_CARVEOUT >= 0) ? PSY_PAIR_CARVEOUT
       : (PARK == 0 ? -1 : (100 * RESIDENT_BLOCKS * (SMEM_BYTES + 1024) + 233471) / 233472);
   __host__ __device__ static constexpr int off(int c) { return c * N - c * (c - 1); }   // first entry of column pair c (row 2c)
@@ -112,9 +125,16 @@ struct FilterPair {
       w[woff(c) + R - 1] = r ? -PSY_AT(R, R - 1) : 1.0;
 #pragma unroll
       for (int k = R - 2; k >= 0; k--) {
+#if PSY_PAIR_WORDER
+        // the newest entry w_{k+1} enters LAST, so that only one FMA of each dot product waits for it
+        double acc = -(w[woff(c) + R] * PSY_AT(R, k));
+#pragma unroll
+        for (int l = R - 1; l >= k + 1; l--) acc = fma(-w[woff(c) + l], PSY_AT(l, k), acc);
+#else
         double acc = -(w[woff(c) + k + 1] * PSY_AT(k + 1, k));
 #pragma unroll
         for (int l = k + 2; l <= R; l++) acc = fma(-w[woff(c) + l], PSY_AT(l, k), acc);
+#endif
         w[woff(c) + k] = acc;
       }
     }

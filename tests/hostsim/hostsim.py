@@ -23,8 +23,6 @@ _CSRC = os.path.join(_ROOT, "psydiff_b200", "csrc")
 _BUILD = os.path.join(_HERE, "_build")
 
 _DRIVER = r"""
-#include <thread>
-#include <vector>
 extern "C" void psy_hostsim_run(const PsyLaunch* L, int block) {
   const int grid = (L->n_inst + block - 1) / block;
   if (psy_lanes_per_instance_in_rk4 == 1) {
@@ -38,22 +36,18 @@ extern "C" void psy_hostsim_run(const PsyLaunch* L, int block) {
       }
     return;
   }
-  // lane-pair kernel: one simulated warp (PSY_SIM_WARP concurrent host threads, cuda_host_shim.h) at a time; warps that hold no
-  // instance are skipped (they would only compute on zeros)
+  // lane-pair kernel: one simulated warp (PSY_SIM_WARP fibers, cuda_host_shim.h) at a time; warps that hold no instance are
+  // skipped (they would only compute on zeros)
+  static const PsyLaunch* launch;
+  launch = L;
+  blockDim.x = (unsigned)block; blockDim.y = blockDim.z = 1;
+  gridDim.x = (unsigned)grid; gridDim.y = gridDim.z = 1;
+  threadIdx.y = threadIdx.z = 0;
   for (int b = 0; b < grid; b++)
     for (int w0 = 0; w0 < block; w0 += PSY_SIM_WARP) {
       if (b * block + w0 >= L->n_inst) continue;
-      std::vector<std::thread> th;
-      for (int l = 0; l < PSY_SIM_WARP; l++)
-        th.emplace_back([=] {
-          blockDim.x = (unsigned)block; blockDim.y = blockDim.z = 1;
-          gridDim.x = (unsigned)grid; gridDim.y = gridDim.z = 1;
-          blockIdx.x = (unsigned)b; blockIdx.y = blockIdx.z = 0;
-          threadIdx.x = (unsigned)(w0 + l); threadIdx.y = threadIdx.z = 0;
-          psy_sim_lane = l; psy_sim_local_sense = psy_sim_ws.sense.load();
-          psy_filter_kernel(*L);
-        });
-      for (auto& t : th) t.join();
+      blockIdx.x = (unsigned)b; blockIdx.y = blockIdx.z = 0;
+      psy_sim_run_warp([](int) { psy_filter_kernel(*launch); }, (unsigned)w0);
     }
 }
 extern "C" int psy_hostsim_block(void) { return psy_block_size; }
@@ -98,7 +92,7 @@ def build(source: str, extra_flags: str = "") -> str:
             f.write('#include "cuda_host_shim.h"\n' + source + _DRIVER)
         # -ffp-contract=fast + -mfma: a*b+c contracts to fma like nvcc's default -fmad=true (not necessarily the same
         # choices: agreement with the device is to rounding, not bit for bit)
-        cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-mfma", "-ffp-contract=fast", "-Wno-unknown-pragmas", "-pthread",
+        cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-mfma", "-ffp-contract=fast", "-Wno-unknown-pragmas",
                "-I", _HERE, "-I", _CSRC] + extra_flags.split() + ["-o", so + f".tmp{os.getpid()}", cpp]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

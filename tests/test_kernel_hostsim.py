@@ -59,7 +59,12 @@ def test_module_info_matches_model():
     assert hs.info[:5] == [0, 1, 6, 6, 30] and hs.info[5] == 0          # rk4, SR, n, m, slots, no shared memory at n = 6
     m8 = pd.newPsydiff(**synth.config_coupled(K=4, N=4, T=4))
     h8 = HostSim(m8)
-    assert h8.info[2] == 8 and h8.info[5] == 2 * (8 + 36) * h8.block * 8    # RK4 state parked in shared memory for n >= 7
+    # n = 8: the lane-pair kernel; x_n and the running sum of ONE lane (m on both lanes + own columns: 8 + 20 doubles) parked in shared memory
+    assert h8.info[2] == 8 and h8.lanes == 2 and h8.block == 64 and h8.info[5] == 2 * (8 + 20) * h8.block * 8
+    h8s = HostSim(m8, "-DPSY_PAIR=0")
+    assert h8s.lanes == 1 and h8s.info[5] == 2 * (8 + 36) * h8s.block * 8   # thread per instance: RK4 state parked for n >= 7
+    m7 = pd.newPsydiff(**synth.config_c4(N=4, T=4))
+    assert HostSim(m7, "-DPSY_PAIR=1").lanes == 2 and hs.lanes == 1        # n = 6: pairs only on request
 
 
 def test_c1_fit_states_gradient_and_golden():
