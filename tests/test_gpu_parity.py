@@ -371,6 +371,34 @@ def test_subsample_4096_persons_at_benchmark_series_length(name):
     _check_grad(pd.newPsydiff(**ks), extended=True, nthreads=nth)
 
 
+def test_lane_pair_kernel_equals_thread_per_instance_kernel_on_ragged_persons():
+    """psy_filter_pair.cuh on the device (n = 8 and n = 10 by default, n = 6 on request): persons of different length and
+    irregular dt inside one warp, instance lists with and without warp alignment, against the thread-per-instance kernel of the
+    same model (-DPSY_PAIR=0) and the oracle."""
+    from psydiff_b200 import _lib
+    for K, flags in ((4, ""), (5, ""), (3, "-DPSY_PAIR=1")):
+        kw = synth.config_coupled(K=K, N=96, T=12, n_groups=3, seed=7 + K)
+        keep = np.ones(96 * 12, dtype=bool)
+        for p in range(0, 96, 5):
+            keep[p * 12 + 1 + (p % 9):(p + 1) * 12] = False          # series of 1..9 rows
+        kw["dataset"] = {k: v[keep] for k, v in kw["dataset"].items()}
+        pair, one = pd.newPsydiff(**kw), pd.newPsydiff(**kw)
+        pd.compileModel(pair, extra_flags=flags)
+        pd.compileModel(one, extra_flags="-DPSY_PAIR=0")
+        L = _lib.lib()
+        assert L.psy_kernel_lanes(pair["_handle"].ptr) == 2 and L.psy_kernel_lanes(one["_handle"].ptr) == 1
+        fa, fb = pd.fitModel(pair), pd.fitModel(one)
+        assert np.max(np.abs(fa["m2LL"] - fb["m2LL"]) / np.abs(fb["m2LL"])) < 1e-12
+        assert np.nanmax(np.abs(fa["latentScores"] - fb["latentScores"])) < 1e-11
+        ga, gb = (np.array(list(pd.getGradients(m).values())) for m in (pair, one))
+        ftot = float(np.abs(np.sum(fb["m2LL"])))
+        assert np.max(np.abs(ga - gb)) < 64 * np.finfo(float).eps * ftot / 2e-6 + 1e-9 * np.max(np.abs(gb))
+        # the oracle in 80 bits (at n >= 8 the double build's own rounding noise reaches the 1e-9 gate on short series, DESIGN.md §5)
+        ext = _oracle(pair, extended=True).fit(nthreads=os.cpu_count() or 1)
+        assert np.max(np.abs(fa["m2LL"] - ext["m2LL"]) / np.abs(ext["m2LL"])) < 1e-10
+        assert np.nanmax(np.abs(fa["latentScores"] - ext["latentScores"])) < 1e-9
+
+
 def test_several_devices_in_one_handle_equal_one_device():
     """psy_model_set_devices: persons cut into work-balanced blocks over the GPUs of the box, one host thread.  Per-person results
     (-2LL, latent scores, predictions) are independent of the cut — bit-identical; parameter sums differ by summation order only

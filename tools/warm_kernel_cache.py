@@ -30,5 +30,5 @@ for modname in ("test_gpu_parity", "test_gpu_examples", "test_gpu_optim", "test_
                     fn(mod.R())
                 else:
                     fn(*a)
-            except Exception as e:
+            except BaseException as e:
                 print(name, a, "->", type(e).__name__, str(e)[:60].replace("\n"," "), flush=True)
