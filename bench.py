@@ -22,6 +22,8 @@ each and land in "configs" with their own kernel time, roofline fraction and ora
 from __future__ import annotations
 
 import argparse
+import contextlib
+import io
 import json
 import os
 import statistics
@@ -534,4 +536,17 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # stdout carries exactly ONE line, the JSON record: whatever libraries print on file descriptor 1 while the bench runs (NCCL's
+    # version banner, for one) goes to stderr; the record is written to the real stdout at the end
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _buf = io.StringIO()
+    with contextlib.redirect_stdout(_buf):
+        main()
+    sys.stdout.flush()
+    _lines = [ln for ln in _buf.getvalue().splitlines() if ln.strip()]
+    for ln in _lines[:-1]:
+        print(ln, file=sys.stderr)
+    if _lines:
+        os.write(_real_stdout, (_lines[-1] + "\n").encode())
