@@ -66,6 +66,8 @@ def parse():
     ap.add_argument("--no-configs", action="store_true", help="skip the C2 / C3 / C5 legs after the C4 timing")
     ap.add_argument("--single-process", action="store_true", help="--gpus N inside ONE process (psy_model_set_devices) instead of torchrun ranks")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--simulate-on-gpu", action="store_true", help="draw the synthetic C4 / C5 observations with torch on this rank's GPU "
+                    "(another random stream than the default numpy one; for builder runs at sizes where numpy takes many minutes)")
     return ap.parse_args()
 
 
@@ -115,19 +117,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_model(name, N, T, rank, id_offset):
+def make_model(name, N, T, rank, id_offset, simulate_on=None):
     """The keyword arguments of newPsydiff for `N` persons of workload `name` (this rank's shard), as a model object whose host
     copy of the dataset is in R's own layout (column-major: what model$data$observations is and what psy_upload takes)."""
     import psydiff_b200 as pd
     from psydiff_b200 import synth
     if name == "C4":
-        kw = synth.config_c4(N=N, T=T, seed=20210132 + rank, id_offset=id_offset)
+        kw = synth.config_c4(N=N, T=T, seed=20210132 + rank, id_offset=id_offset, simulate_on=simulate_on)
     elif name == "C2":
         kw = synth.config_c2(N=N, T=T, seed=20210130 + rank)
     elif name == "C3":
         kw = synth.config_c3(N=N, T=T, seed=20210131 + rank, id_offset=id_offset)
     elif name == "C5":
-        kw = synth.config_c5(N=N, T=T, seed=20210133 + rank, id_offset=id_offset)
+        kw = synth.config_c5(N=N, T=T, seed=20210133 + rank, id_offset=id_offset, simulate_on=simulate_on)
     else:
         raise ValueError(name)
     model = pd.newPsydiff(**kw)
@@ -418,7 +420,8 @@ def main():
 
     npg = persons_of(args, ctx.n_gpus)
     n_local = npg * ctx.in_process
-    model = make_model("C4", n_local, args.timepoints, rank, rank * n_local)
+    model = make_model("C4", n_local, args.timepoints, rank, rank * n_local,
+                       simulate_on=f"cuda:{ctx.local}" if args.simulate_on_gpu else None)
     compile_on_devices(ctx, model)
     h = model["_handle"].ptr
     pt = model["pars"]["parameterTable"]
@@ -494,7 +497,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.n_gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "dtype": "f64", "data": "synthetic (torch random stream, drawn on the GPU)" if args.simulate_on_gpu else "synthetic",
         "config": {
             "workload": f"C4: {WORKLOADS['C4']['desc']}, P={P} ({inst_per_person:.0f} filter instances/person), {npg} persons/GPU x T={T} "
                         f"({N_total} persons total), -2LL + full central FD gradient, eps=1e-6 "

@@ -90,7 +90,7 @@ def _vdp3_drift(x, mu, om, k):
     return dx
 
 
-def config_c4(N=1_000_000, T=100, seed=20210132, n_groups=8, id_offset=0, **settings):
+def config_c4(N=1_000_000, T=100, seed=20210132, n_groups=8, id_offset=0, simulate_on=None, **settings):
     """C4: three diffusively coupled Van der Pol oscillators (n = m = 6, y = x), irregular time intervals,
     mu1..mu3 specific to 8 groups (P = 3*8 + 27 = 51 parameters, 30 per person -> 61 filter instances per person),
     fixed-step RK4 with the package default h = min(dt>0)/30."""
@@ -107,7 +107,10 @@ def config_c4(N=1_000_000, T=100, seed=20210132, n_groups=8, id_offset=0, **sett
     obs = np.empty((N, T, 6))
     CH = 65536
     sub = 0.05
-    for c0 in range(0, N, CH):
+    if simulate_on is not None:                    # same scheme with torch ops on the named device (bench.py --simulate-on-gpu)
+        gain = {(0, 1): kk[0], (0, 2): kk[1], (1, 0): kk[2], (1, 2): kk[3], (2, 0): kk[4], (2, 1): kk[5]}
+        obs[:] = _simulate_coupled_torch(simulate_on, seed, m0, mu_g[group - 1], om, gain, dts, ldiff, rsd, sub)
+    for c0 in range(0, N if simulate_on is None else 0, CH):
         c1 = min(N, c0 + CH)
         nb = c1 - c0
         mu = mu_g[group[c0:c1] - 1]
@@ -179,10 +182,58 @@ def config_c3(N=250_000, T=100, seed=20210131, id_offset=0, **settings):
     return kw
 
 
-def config_coupled(K=4, N=1000, T=100, seed=20210133, n_groups=8, id_offset=0, **settings):
+_ONE_STREAM = 65536          # up to here a dataset is simulated from one random stream (bit-stable small cases)
+_BLOCK = 8192
+
+
+def _sim_threads():
+    """Threads for the data simulation of one rank: the host's cores divided by the ranks of this node."""
+    import os
+    return max(1, min(8, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+
+
+def _simulate_coupled_torch(device, seed, m0, mu, om, gain, dts, ldiff, rsd, sub):
+    """Heun / Euler-Maruyama simulation of config_coupled's data with torch ops on `device` (synthetic data only: the random
+    stream is torch's, so the values differ from the numpy path's; minutes of numpy become a second on the GPU)."""
+    import torch
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev).manual_seed(int(seed))
+    N, T = dts.shape
+    n = m0.shape[0]
+    K = n // 2
+    f64 = dict(dtype=torch.float64, device=dev)
+    mu_t, om2, dts_t = torch.as_tensor(mu, **f64), torch.as_tensor(om * om, **f64)[None, :], torch.as_tensor(dts, **f64)
+    G = torch.zeros(K, K, **f64)                   # acc_i += sum_j g_ij (q_j - q_i)  ==  q @ G^T - rowsum(G) * q
+    for (i, j), g in gain.items():
+        G[i, j] = g
+    Gs = G.sum(1)[None, :]
+
+    def drift(x):
+        q, v = x[:, 0::2], x[:, 1::2]
+        dx = torch.empty_like(x)
+        dx[:, 0::2] = v
+        dx[:, 1::2] = mu_t * (1.0 - q * q) * v - om2 * q + q @ G.T - Gs * q
+        return dx
+    randn = lambda: torch.randn(N, n, generator=gen, **f64)
+    x = torch.as_tensor(m0, **f64)[None, :] + 0.5 * randn()
+    obs = torch.empty(N, T, n, **f64)
+    for t in range(T):
+        rem = dts_t[:, t].clone()
+        for _ in range(int(np.ceil(float(rem.max()) / sub)) if t > 0 else 0):
+            h = torch.clamp(rem, max=sub)
+            rem -= h
+            k1 = drift(x)
+            k2 = drift(x + h[:, None] * k1)
+            x = x + 0.5 * h[:, None] * (k1 + k2) + ldiff * torch.sqrt(h)[:, None] * randn()
+        obs[:, t, :] = x + rsd * randn()
+    return obs.cpu().numpy()
+
+
+def config_coupled(K=4, N=1000, T=100, seed=20210133, n_groups=8, id_offset=0, simulate_on=None, **settings):
     """C5 family: K diffusively coupled Van der Pol oscillators on a ring with all-to-all coupling gains
     (n = m = 2K; K = 4 is the 8-latent model of config 5, its 12 coupling gains are the lasso targets of the GIST fit).
-    mu_i group-specific as in C4, irregular dt, rk4 with the package default step."""
+    mu_i group-specific as in C4, irregular dt, rk4 with the package default step.  `simulate_on` = a torch device string
+    simulates the observations there instead of in numpy (examples/c5_gist_fit.py at 125 000 persons per GPU)."""
     rng = np.random.default_rng(seed)
     n = 2 * K
     ids = id_offset + np.arange(1, N + 1)
@@ -208,17 +259,28 @@ def config_coupled(K=4, N=1000, T=100, seed=20210133, n_groups=8, id_offset=0, *
         return dx
     obs = np.empty((N, T, n))
     sub = 0.05
-    x = m0[None, :] + 0.5 * rng.standard_normal((N, n))
-    mu = mu_g[group - 1]
-    for t in range(T):
-        rem = dts[:, t].copy()
-        for _ in range(int(np.ceil(rem.max() / sub)) if t > 0 else 0):
-            h = np.minimum(rem, sub)
-            rem -= h
-            k1 = drift(x, mu)
-            k2 = drift(x + h[:, None] * k1, mu)
-            x = x + 0.5 * h[:, None] * (k1 + k2) + ldiff * np.sqrt(h)[:, None] * rng.standard_normal((N, n))
-        obs[:, t, :] = x + rsd * rng.standard_normal((N, n))
+
+    def simulate(c0, c1, rng):
+        x = m0[None, :] + 0.5 * rng.standard_normal((c1 - c0, n))
+        mu = mu_g[group[c0:c1] - 1]
+        for t in range(T):
+            rem = dts[c0:c1, t].copy()
+            for _ in range(int(np.ceil(rem.max() / sub)) if t > 0 else 0):
+                h = np.minimum(rem, sub)
+                rem -= h
+                k1 = drift(x, mu)
+                k2 = drift(x + h[:, None] * k1, mu)
+                x = x + 0.5 * h[:, None] * (k1 + k2) + ldiff * np.sqrt(h)[:, None] * rng.standard_normal((c1 - c0, n))
+            obs[c0:c1, t, :] = x + rsd * rng.standard_normal((c1 - c0, n))
+    if simulate_on is not None:                    # C5 at its stated size: the same scheme in torch on the named device
+        obs[:] = _simulate_coupled_torch(simulate_on, seed, m0, mu_g[group - 1], om, gain, dts, ldiff, rsd, sub)
+    elif N <= _ONE_STREAM:
+        simulate(0, N, rng)                        # one random stream: what every fixture and the bench's C5 shard were made with
+    else:                                          # C5 at its stated size: cache-sized person blocks, one stream each, on a few threads
+        from concurrent.futures import ThreadPoolExecutor
+        blocks = [(c0, min(N, c0 + _BLOCK)) for c0 in range(0, N, _BLOCK)]
+        with ThreadPoolExecutor(max_workers=_sim_threads()) as pool:
+            list(pool.map(lambda b: simulate(b[0], b[1], np.random.default_rng([seed, b[0]])), blocks))
     lines = []
     parameters = {}
     for i in range(K):
