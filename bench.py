@@ -297,7 +297,8 @@ def kernel_roofline(name, model, n_inst, n_persons, kernel_ms, peak, calib, T):
         qd = np.round(dtv, 3)                      # dt values are continuous; bin to 1e-3 for the step tally
         udt, cnt = np.unique(qd, return_counts=True)
         steps_of = np.array([flops.rk4_step_count(float(d), hstep) if d != 0 else 0 for d in udt])
-        steps_pp = float((steps_of * cnt).sum()) / n_persons
+        # tally over the model's whole dataset (all devices of this process), per person of it
+        steps_pp = float((steps_of * cnt).sum()) / model["pars"]["parameterTable"].theta_index.shape[0]
         fl_formula = flops.kernel_flops(w["n"], w["m"], w["Ff"], w["Fh"], steps_pp, T, l_diag=True, dep=codegen.drift_dependency(model["_spec"]))
         out["rk4_steps_per_interval"] = steps_pp / max(T - 1, 1)
         out["flops_per_instance_loop_count"] = fl_formula
