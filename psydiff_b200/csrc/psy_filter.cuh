@@ -103,6 +103,10 @@ __device__ __forceinline__ double rsq(double x) {
 #ifndef PSY_RSQRT_ROT
 #define PSY_RSQRT_ROT (-1)
 #endif
+#ifndef PSY_DOPRI_LEAN
+#define PSY_DOPRI_LEAN 1   // 1 (default): step-size controller of the adaptive stepper without libdevice pow and IEEE division (below);
+                           // C3 on B200: 112.0 -> 90.9 ms (profiles/r02n_variants.txt).  0 = pow() and '/' as odeint writes them
+#endif
 
 template <class Mdl>
 struct Filter {
@@ -651,6 +655,18 @@ struct Filter {
 #ifndef PSY_RK4_SMEM
 #define PSY_RK4_SMEM (-1)
 #endif
+#ifndef PSY_STEP_UNROLL
+#define PSY_STEP_UNROLL 1
+#endif
+#ifndef PSY_STAGE_UNROLL
+#define PSY_STAGE_UNROLL 0   // RK4 stages per loop body (1, 2 or 4; 0 = by model size): > 1 lets ptxas schedule across stage boundaries
+#endif                       // and drop the dead stage-input update of the 4th stage, at 2x / 4x the hot loop's code size.  Measured on
+                             // B200 (profiles/r02m_stage_unroll.txt, r02n_variants.txt): n = 2 (C2) 139.4 -> 127.6 ms with 4 stages per body (311 instructions), n = 4 306.2 -> 290.2 ms;
+                             // n = 6 605 -> 609 (2) / 723 ms (4) and the n = 8 lane-pair kernel 1296 -> 1547 (2) / 2180 ms (4): a stage loop of more than
+                             // 32 KB of SASS (2000 instructions) no longer fits the L1.5 instruction cache that 8 warps at different
+                             // positions of the loop share
+  static constexpr int STAGE_UNROLL = (PSY_STAGE_UNROLL > 0) ? PSY_STAGE_UNROLL : (N <= 4 ? 4 : 1);
+  static constexpr int STEP_UNROLL = PSY_STEP_UNROLL;   // RK4 steps per loop body of the register-resident path (experiment knob)
   static constexpr bool RK4_SMEM = (PSY_RK4_SMEM == 1) || (PSY_RK4_SMEM == -1 && N >= 7);
   static constexpr int SMEM_BYTES = RK4_SMEM ? 2 * (N + TN) * BLOCK * 8 : 0;
   static __device__ __forceinline__ void rk4(const double (&p)[F], double (&m)[N], double (&A)[TN],
@@ -668,7 +684,10 @@ struct Filter {
 #pragma unroll
         for (int i = 0; i < TN; i++) { sx[(N + i) * BLOCK] = A[i]; sa[(N + i) * BLOCK] = A[i]; }
 #pragma unroll 1
-        for (int st = 0; st < 4; st++) {
+        for (int sp = 0; sp < 4 / STAGE_UNROLL; sp++)
+#pragma unroll
+        for (int su = 0; su < STAGE_UNROLL; su++) {
+          const int st = sp * STAGE_UNROLL + su;
           double km[N], kA[TN];
           const double tc = (st == 0) ? t0 : ((st == 3) ? t0 + h : t0 + 0.5 * h);
           const double b = (st == 0 || st == 3) ? h * (1.0 / 6.0) : h * (1.0 / 3.0);
@@ -714,7 +733,7 @@ struct Filter {
         }
       }
     } else {
-#pragma unroll 1
+#pragma unroll STEP_UNROLL
       for (int step = 0; step < K; step++) {
         const double t0 = (double)step * h;
         double mt[N], At[TN], ma[N], Aa[TN];
@@ -723,7 +742,10 @@ struct Filter {
 #pragma unroll
         for (int i = 0; i < TN; i++) { At[i] = A[i]; Aa[i] = A[i]; }
 #pragma unroll 1
-        for (int st = 0; st < 4; st++) {
+        for (int sp = 0; sp < 4 / STAGE_UNROLL; sp++)
+#pragma unroll
+        for (int su = 0; su < STAGE_UNROLL; su++) {
+          const int st = sp * STAGE_UNROLL + su;
           double km[N], kA[TN];
           const double tc = (st == 0) ? t0 : ((st == 3) ? t0 + h : t0 + 0.5 * h);
           const double b = (st == 0 || st == 3) ? h * (1.0 / 6.0) : h * (1.0 / 3.0);
@@ -771,7 +793,30 @@ struct Filter {
         reinterpret_cast<double(&)[N]>(k[0]), reinterpret_cast<double(&)[TN]>(k[N]), Q, ut, person, t);
   }
   static __device__ __forceinline__ double err_entry(double xe, double x, double dx, double dt) {
+#if PSY_DOPRI_LEAN
+    return fabs(xe) * rcp(1e-6 + 1e-6 * (fabs(x) + fabs(dt) * fabs(dx)));
+#else
     return fabs(xe) / (1e-6 + 1e-6 * (fabs(x) + fabs(dt) * fabs(dx)));
+#endif
+  }
+  // x^(-1/3) and x^(-1/5) of the step-size controller.  PSY_DOPRI_LEAN: single-precision seed (lg2 / ex2 on the special-function unit,
+  // relative error <= 1e-6) and two Newton steps on y^-k = x (quadratic: 1e-6 -> 1e-12 -> 1e-16 before rounding) instead of libdevice's
+  // pow (two call sites of ~190 instructions each).  The controller only scales dt with these, accept / reject is decided by err itself.
+  template <int KPOW>
+  static __device__ __forceinline__ double inv_root(double x) {
+#if PSY_DOPRI_LEAN && defined(__CUDA_ARCH__)
+    double y = (double)exp2f(log2f((float)x) * (-1.0f / (float)KPOW));
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+      double yk = y * y;                               // y^2
+      if constexpr (KPOW == 3) yk = yk * y;            // y^3
+      else yk = yk * yk * y;                           // y^5
+      y = y * fma(-x, yk, (double)(KPOW + 1)) * (1.0 / (double)KPOW);
+    }
+    return y;
+#else
+    return pow(x, -1.0 / (double)KPOW);
+#endif
   }
   static __device__ void dopri5(const double (&p)[F], double (&m)[N], double (&A)[TN], const double (&Q)[QLEN],
                                              const UT& ut, int person, double t1, double dt) {
@@ -837,11 +882,11 @@ struct Filter {
         }
         if (bad) { dead = true; break; }
         if (err > 1.0) {
-          dt *= fmax(0.9 * pow(err, -1.0 / 3.0), 0.2);
+          dt *= fmax(0.9 * inv_root<3>(err), 0.2);
           continue;
         }
         t += dt;
-        if (err < 0.5) dt *= 0.9 * pow(fmax(3.2e-4, err), -1.0 / 5.0);  // 5^-5 = 3.2e-4
+        if (err < 0.5) dt *= 0.9 * inv_root<5>(fmax(3.2e-4, err));  // 5^-5 = 3.2e-4
 #pragma unroll
         for (int i = 0; i < NS; i++) { z[i] = zn[i]; k1[i] = k7[i]; }
         break;

@@ -79,6 +79,7 @@ struct FilterPair {
   static constexpr bool ENABLED = ELIGIBLE && (PSY_PAIR == 1 || (PSY_PAIR == -1 && N >= 8));
   static constexpr int BLOCK = PSY_PAIR_BLOCK;
   static constexpr int PARK = PSY_PAIR_PARK;
+  static constexpr int STAGE_UNROLL = (PSY_STAGE_UNROLL > 0) ? PSY_STAGE_UNROLL : 1;   // see psy_filter.cuh: the pair loop is 18 KB of SASS already
   static constexpr int SMEM_BYTES = PARK * NS * BLOCK * 8;
   // shared-memory carveout (percent of 228 KB) that lets the 65536 / (256 · BLOCK) blocks the register file holds be resident
   static constexpr int MIN_BLOCKS = PSY_PAIR_MIN_BLOCKS;
@@ -250,7 +251,10 @@ struct FilterPair {
         if constexpr (PARK >= 2) sa[i * BLOCK] = v; else ac[i] = v;
       }
 #pragma unroll 1
-      for (int st = 0; st < 4; st++) {
+      for (int sp = 0; sp < 4 / STAGE_UNROLL; sp++)
+#pragma unroll
+      for (int su = 0; su < STAGE_UNROLL; su++) {
+        const int st = sp * STAGE_UNROLL + su;
         double km[N], kA[TP], rdj[NP];
         const double tc = (st == 0) ? t0 : ((st == 3) ? t0 + h : t0 + 0.5 * h);
         const double b = (st == 0 || st == 3) ? h * (1.0 / 6.0) : h * (1.0 / 3.0);
