@@ -193,6 +193,7 @@ struct Shard {
   int64_t n_inst = 0, n_inst_real = 0, n_pairs = 0, n_chunks = 0, n_small = 0, n_big = 0;
   double ksteps_h = -1.0;
   bool slots_ready = false;
+  int lists_N = -1;           // persons the K2 lists of this shard were built for
   double last_ms = 0.0;
   int64_t last_instances = 0;
   int* h_nsel = nullptr;         // pinned: selected-instance count of a restricted sweep
@@ -385,7 +386,11 @@ int distribute(psy_model* M) {
     RC_TRY(use(s));
     s.p0 = cut[k]; s.N = cut[k + 1] - cut[k];
     s.r0 = M->h_row_off[s.p0]; s.rows = M->h_row_off[s.p0 + s.N] - s.r0;
-    s.ksteps_h = -1.0; s.slots_ready = false; s.n_inst = s.n_inst_real = 0;
+    s.ksteps_h = -1.0;
+    // The lists K2 builds depend on the slot map and on WHICH persons a device holds, not on their rows: with one device (all persons,
+    // always) a re-upload of the same persons keeps them; with several devices the work-balanced cuts may move, so they are rebuilt.
+    const bool keep_lists = M->sh.size() == 1 && s.slots_ready && M->have_slots && s.lists_N == s.N;
+    if (!keep_lists) { s.slots_ready = false; s.n_inst = s.n_inst_real = 0; }
     RC_TRY(s.d_obs.alloc((size_t)s.rows * m));
     RC_TRY(s.d_dt.alloc((size_t)s.rows));
     RC_TRY(s.d_row_off.alloc((size_t)s.N + 1));
@@ -498,6 +503,7 @@ int build_slots_on(psy_model* M, Shard& s) {
 #undef K2_CU
   cleanup2();
   s.slots_ready = true;
+  s.lists_N = N;
   return PSY_OK;
 }
 
@@ -765,7 +771,10 @@ int psy_upload(psy_model* M, int64_t rows, int N, const double* obs_cm, const do
   M->rows = rows; M->N = N;
   M->have_data = true;
   RC_TRY(distribute(M));
-  if (M->have_slots) RC_TRY(build_slots(M));   // same persons, new rows: the person blocks may have moved between devices
+  if (M->have_slots) {   // same persons, new rows: the person blocks may have moved between devices (never with one device)
+    bool kept = M->sh.size() == 1 && M->sh[0].slots_ready;
+    if (!kept) RC_TRY(build_slots(M));
+  }
   return PSY_OK;
 }
 
