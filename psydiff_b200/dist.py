@@ -100,7 +100,8 @@ def getGradientsSharded(psydiffModel, group=None, return_total: bool = False):
     g = np.empty(P)
     tot = C.c_double(0.0)
     _lib.check(L.psy_grad_finish(h.ptr, direction, _lib.dptr(g), C.byref(tot)))
-    out: Dict[str, float] = {l: float(v) for l, v in zip(pt.theta_labels, g)}
+    from .model import NamedVector
+    out = NamedVector(pt.theta_labels, g, getattr(pt, "_label_pos", None))
     return (out, tot.value) if return_total else out
 
 
