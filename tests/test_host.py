@@ -579,3 +579,31 @@ def test_typed_temporaries_and_expm_compile_for_the_device():
     bad["latentEquations"] = "arma::mat T(2, 2);\n" + bad["latentEquations"]   # a size-only declaration has no device counterpart
     with pytest.raises(PsydiffError, match="unsupported on device"):
         pd.compileModelSource(pd.newPsydiff(**bad))
+
+
+def test_named_vector_reads_like_a_dict():
+    """getGradients returns a NamedVector (R's named numeric): dict semantics without per-entry objects until asked for."""
+    from psydiff_b200.model import NamedVector
+    v = NamedVector(["a", "b", "c"], np.array([1.0, np.nan, 3.0]))
+    assert v["a"] == 1.0 and np.isnan(v["b"]) and len(v) == 3 and "c" in v and "z" not in v
+    assert list(v) == ["a", "b", "c"] and list(v.keys()) == ["a", "b", "c"]
+    assert v.values()[2] == 3.0 and isinstance(v.values()[0], float)
+    assert dict(v.items())["c"] == 3.0 and set(dict(v)) == {"a", "b", "c"}
+    assert np.array_equal(np.asarray(v), [1.0, np.nan, 3.0], equal_nan=True)
+    assert np.array_equal(np.array(list(v.values())), np.asarray(v), equal_nan=True)
+    w = NamedVector(["x", "y"], [2.0, 4.0], {"x": 0, "y": 1})
+    assert w == {"x": 2.0, "y": 4.0} and {"x": 2.0, "y": 4.0} == w and w.get("q", 7.0) == 7.0
+    with pytest.raises(KeyError):
+        w["q"]
+    with pytest.raises(TypeError):
+        w["x"] = 1.0                                   # read-only, like the named vector R hands back
+
+
+def test_synthetic_data_can_be_drawn_with_torch():
+    """simulate_on = a torch device: the same simulation scheme with torch ops (examples/c5_gist_fit.py and bench.py --simulate-on-gpu
+    use it on the GPU, where numpy needs minutes); another random stream, the same distribution."""
+    for cfg in (synth.config_c4, synth.config_c5):
+        a = cfg(N=400, T=12, seed=3)["dataset"]["observations"]
+        b = cfg(N=400, T=12, seed=3, simulate_on="cpu")["dataset"]["observations"]
+        assert a.shape == b.shape and np.isfinite(b).all()
+        assert np.allclose(a.mean(0), b.mean(0), atol=0.15) and np.allclose(a.std(0), b.std(0), rtol=0.15)

@@ -213,7 +213,8 @@ def test_instance_list_padding_and_parameter_sets_do_not_change_results():
         assert np.array_equal(many[k], hs.fit(theta=sets[k], states=False)["m2LL"])
 
 
-@pytest.mark.parametrize("flags", ["-DPSY_RHS_SCALED=0", "-DPSY_RK4_SMEM=1", "-DPSY_RK4_SMEM=0", "-DPSY_IEEE_DIV", "-DPSY_RSQRT_ROT"])
+@pytest.mark.parametrize("flags", ["-DPSY_RHS_SCALED=0", "-DPSY_RK4_SMEM=1", "-DPSY_RK4_SMEM=0", "-DPSY_IEEE_DIV", "-DPSY_RSQRT_ROT",
+                                   "-DPSY_STAGE_UNROLL=2", "-DPSY_STAGE_UNROLL=4", "-DPSY_STEP_UNROLL=2"])
 def test_compile_time_variants_agree(flags):
     """Every compile-time variant of the kernel computes the same filter (to rounding)."""
     for kw in (synth.config_c4(N=4, T=8), synth.config_coupled(K=4, N=3, T=6)):
@@ -221,6 +222,20 @@ def test_compile_time_variants_agree(flags):
         a = HostSim(model).fit()["m2LL"]
         b = HostSim(model, flags).fit()["m2LL"]
         assert np.max(np.abs(a - b) / np.abs(a)) < 1e-11
+
+
+def test_stage_unrolling_and_the_lean_dopri5_controller_change_nothing_but_rounding():
+    """RK4 stages per loop body: the default is 4 for n <= 4 and 1 above; 1, 2 and 4 give the same filter at n = 2 (bit for bit on
+    the host, where nothing is re-associated).  The adaptive stepper with odeint's own pow() and '/' in the step-size controller
+    (-DPSY_DOPRI_LEAN=0) against the default branch-free reciprocal: same accepted steps, -2LL equal to rounding."""
+    model = pd.newPsydiff(**synth.config_c1(N=6, T=12))
+    a = HostSim(model).fit()["m2LL"]
+    for flags in ("-DPSY_STAGE_UNROLL=1", "-DPSY_STAGE_UNROLL=2"):
+        assert np.array_equal(a, HostSim(model, flags).fit()["m2LL"])
+    for kw in (synth.config_c1(N=6, T=12, integrateFunction="runge_kutta_dopri5"), synth.config_c3(N=6, T=12)):
+        model = pd.newPsydiff(**kw)
+        lean, plain = HostSim(model).fit()["m2LL"], HostSim(model, "-DPSY_DOPRI_LEAN=0").fit()["m2LL"]
+        assert np.max(np.abs(lean - plain) / np.abs(plain)) < 1e-12
 
 
 @pytest.mark.parametrize("name", ["c1", "c1_missing_cov", "c3", "c4", "c4_T100", "n8"])
