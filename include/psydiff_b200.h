@@ -112,7 +112,9 @@ int psy_model_settings(psy_model* mdl, double alpha, double beta, double kappa, 
 
 /* model$data (R/prepareModel.R:413-426, R/modelTemplate.R:201-206): observations rows x m COLUMN-major with
  * NaN/NA = missing, dt[rows], persons as N contiguous row blocks (person_off[N+1]) with their id values.
- * The data stays resident in HBM across all later calls. */
+ * The data stays resident in HBM across all later calls.  Calling it again with the same number of persons replaces the rows
+ * and keeps the slot map; with one device the instance / pair / chunk lists of psy_set_slots are kept too (they depend on the
+ * slot map, not on the rows), with several devices they are rebuilt because the work-balanced person cuts may move. */
 int psy_upload(psy_model* mdl, int64_t rows, int n_persons, const double* observations_colmajor, const double* dt,
                const int64_t* person_off, const int* person_id);
 
