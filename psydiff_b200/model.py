@@ -653,9 +653,10 @@ class NamedVector(Mapping):
         return "NamedVector({" + head + (", ..." if len(self._labels) > 6 else "") + "})"
 
 
-def getGradients(psydiffModel) -> Dict[str, float]:
+def getGradients(psydiffModel) -> "NamedVector":
     """getGradients (R/modelTemplate.R:852-930): finite-difference gradient of Σ -2LL for every parameter, with the
-    eps[] fallback; all 2P+1 filter sweeps run as one batched launch per eps level.  The model is not modified."""
+    eps[] fallback; all 2P+1 filter sweeps run as one batched launch per eps level.  The model is not modified.  Returns the
+    gradient as a named vector (NamedVector: reads like {label: value}, R's names(gradients)))."""
     h = _push_settings(psydiffModel)
     pt = psydiffModel["pars"]["parameterTable"]
     theta = np.ascontiguousarray(pt.theta_values, dtype=np.float64)
@@ -702,6 +703,6 @@ def stopParallelGradients(psydiffModel):
     psydiffModel["cl"] = None
 
 
-def getGradientsParallel(psydiffModel) -> Dict[str, float]:
+def getGradientsParallel(psydiffModel) -> "NamedVector":
     """getGradientsParallel (R/prepareModel.R:608-616): same result as getGradients, ordered by names(pars)."""
     return getGradients(psydiffModel)
