@@ -1,7 +1,12 @@
 """Cross-check of a GPU bench line on the CPU: Σ-2LL of the benchmark shard that `python bench.py --persons-per-gpu N` filtered on
-the B200 (its `check.m2ll_total`) against the SAME kernel source compiled for the host (tests/hostsim), all N persons x T = 100.
+the B200 (its `check.m2ll_total`), all N persons x T = 100, against
+  * the SAME kernel source compiled for the host (tests/hostsim) — default: arithmetic of the device build vs the host build, or
+  * the ORACLE (`--oracle`: oracle/psy_oracle.cpp, the CPU restatement of the reference's algorithm) — parity at benchmark scale.
 
-    python tools/bench_total_crosscheck.py profiles/r01f_bench_8192persons_1gpu.json
+    python tools/bench_total_crosscheck.py profiles/r01f_bench_8192persons_1gpu.json [--oracle] [--config C2|C3|C5]
+
+`--config` checks one of the side legs of the line (`configs.<name>.check.m2ll_total`: C2 100 000 persons, C3 250 000 persons under
+the adaptive stepper, C5's model 16 384 persons) instead of the C4 headline shard.
 
 Recorded result (r01f, 8192 persons x 100 time points, about 62 RK4 steps per interval): GPU 4773326.782180222, host-compiled kernel
 source 4773326.78218022 — relative difference 3.9e-16 (30 s on 8 host cores); r01e, the default 125 000-person shard:
@@ -22,27 +27,62 @@ import psydiff_b200 as pd  # noqa: E402
 from psydiff_b200 import synth  # noqa: E402
 
 
+_KW = None          # the shard's newPsydiff arguments, made once in the parent (the workers are forked from it)
+_ORACLE = False
+
+
+def shard_kwargs(name, N, T):
+    """newPsydiff arguments of bench.py's rank-0 shard of workload `name` (bench.make_model)."""
+    if name == "C4":
+        return synth.config_c4(N=N, T=T, seed=20210132, id_offset=0)
+    if name == "C2":
+        return synth.config_c2(N=N, T=T, seed=20210130)
+    if name == "C3":
+        return synth.config_c3(N=N, T=T, seed=20210131, id_offset=0)
+    if name == "C5":
+        return synth.config_c5(N=N, T=T, seed=20210133, id_offset=0)
+    raise SystemExit(f"unknown config {name}")
+
+
 def work(args):
     lo, hi, N, T = args
-    from hostsim.hostsim import HostSim
-    kw = synth.config_c4(N=N, T=T, seed=20210132, id_offset=0)          # bench.py's rank-0 shard
+    kw = dict(_KW)
     ds = kw["dataset"]
-    mn = np.min(ds["dt"][ds["dt"] > 0])
-    kw["timeStep"] = np.linspace(mn / 30, mn / 10, 5)                    # the step of the WHOLE shard (R/prepareModel.R:435-438)
+    if "timeStep" not in kw:
+        mn = np.min(ds["dt"][ds["dt"] > 0])
+        kw["timeStep"] = np.linspace(mn / 30, mn / 10, 5)                # the step of the WHOLE shard (R/prepareModel.R:435-438)
     kw["dataset"] = {k: v[lo * T:hi * T] for k, v in ds.items()}
-    return lo, HostSim(pd.newPsydiff(**kw)).fit(states=False)["m2LL"]
+    model = pd.newPsydiff(**kw)
+    if _ORACLE:
+        from oracle.oracle import Oracle
+        return lo, Oracle(model).fit()["m2LL"]
+    from hostsim.hostsim import HostSim
+    return lo, HostSim(model).fit(states=False)["m2LL"]
 
 
 def main():
+    global _KW, _ORACLE
+    _ORACLE = "--oracle" in sys.argv[2:]
     line = json.load(open(sys.argv[1]))
-    N, T = int(line["config"]["persons_per_gpu"]), int(line["config"]["timepoints"])
-    gpu = float(line["check"]["m2ll_total"])
+    name = sys.argv[sys.argv.index("--config") + 1].upper() if "--config" in sys.argv else "C4"
+    T = int(line["config"]["timepoints"])
+    if name == "C4":
+        N, gpu = int(line["config"]["persons_per_gpu"]), float(line["check"]["m2ll_total"])
+    else:
+        N, gpu = int(line["configs"][name]["persons"]), float(line["configs"][name]["check"]["m2ll_total"])
     t0 = time.time()
-    step = max(64, N // 16)
-    with Pool(min(8, os.cpu_count() or 1)) as p:
+    _KW = shard_kwargs(name, N, T)                                      # bench.py's rank-0 shard
+    if _ORACLE:
+        from oracle import oracle as orc
+        orc.build()
+    step = max(64, N // 64)
+    with Pool(min(16, os.cpu_count() or 1)) as p:
         res = sorted(p.map(work, [(i, min(i + step, N), N, T) for i in range(0, N, step)]))
-    tot = float(np.sum(np.concatenate([r[1] for r in res])))
-    print(f"persons {N} x T {T}: GPU {gpu!r}  host-compiled kernel source {tot!r}  relative difference {abs(tot - gpu) / abs(gpu):.2e}  ({time.time() - t0:.0f} s)")
+    per = np.concatenate([r[1] for r in res])
+    tot = float(np.sum(per))
+    what = "oracle (CPU restatement of the reference)" if _ORACLE else "host-compiled kernel source"
+    print(f"{name}: persons {N} x T {T}: GPU {gpu!r}  {what} {tot!r}  relative difference {abs(tot - gpu) / abs(gpu):.2e}  "
+          f"(non-finite persons: {int((~np.isfinite(per)).sum())}; {time.time() - t0:.0f} s)")
 
 
 if __name__ == "__main__":
