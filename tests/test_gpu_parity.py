@@ -399,6 +399,28 @@ def test_lane_pair_kernel_equals_thread_per_instance_kernel_on_ragged_persons():
         assert np.nanmax(np.abs(fa["latentScores"] - ext["latentScores"])) < 1e-9
 
 
+def test_stage_unrolling_and_the_lean_dopri5_controller_on_the_device():
+    """The late round-2 kernel defaults against their plain forms, on the device: four RK4 stages per loop body (n <= 4) against the
+    rolled stage loop, and the adaptive stepper's step-size controller without libdevice pow / IEEE division against odeint's
+    own formulas (-DPSY_DOPRI_LEAN=0) — same filter to rounding, both within the gate against the oracle."""
+    for kw in (synth.config_c1(N=64, T=20), synth.config_coupled(K=2, N=32, T=10, n_groups=2)):
+        a, b = pd.newPsydiff(**kw), pd.newPsydiff(**kw)
+        pd.compileModel(a)
+        pd.compileModel(b, extra_flags="-DPSY_STAGE_UNROLL=1")
+        fa, fb = pd.fitModel(a)["m2LL"], pd.fitModel(b)["m2LL"]
+        assert np.max(np.abs(fa - fb) / np.abs(fb)) < 1e-13
+        ga, gb = (np.array(list(pd.getGradients(m).values())) for m in (a, b))
+        assert np.max(np.abs(ga - gb)) <= 64 * np.finfo(float).eps * float(np.abs(fb.sum())) / 2e-6 + 1e-9 * np.max(np.abs(gb))
+    for kw in (synth.config_c3(N=64, T=24), synth.config_c1(N=32, T=20, integrateFunction="runge_kutta_dopri5")):
+        lean, plain = pd.newPsydiff(**kw), pd.newPsydiff(**kw)
+        pd.compileModel(lean)
+        pd.compileModel(plain, extra_flags="-DPSY_DOPRI_LEAN=0")
+        fl, fp = pd.fitModel(lean)["m2LL"], pd.fitModel(plain)["m2LL"]
+        assert np.max(np.abs(fl - fp) / np.abs(fp)) < 1e-11
+        ref = _oracle(lean).fit()["m2LL"]
+        assert np.max(np.abs(fl - ref) / np.abs(ref)) < M2LL_RTOL and np.max(np.abs(fp - ref) / np.abs(ref)) < M2LL_RTOL
+
+
 def test_several_devices_in_one_handle_equal_one_device():
     """psy_model_set_devices: persons cut into work-balanced blocks over the GPUs of the box, one host thread.  Per-person results
     (-2LL, latent scores, predictions) are independent of the cut — bit-identical; parameter sums differ by summation order only
